@@ -1,0 +1,174 @@
+/* speech_recog.h -- C-ABI of libspeech_b200.so, the B200-native drop-in for the reference's
+ * VAD -> MFCC -> DTW hot path (gk969/stm32-speech-recognition, Src/Speech_Recog + the FFT asm).
+ *
+ * Two layers, both plain C (pointers and sizes only, no CUDA/torch types in any signature):
+ *
+ *  (1) The reference's own entry points, same names / argument order / struct layouts, each a
+ *      batch-of-1 launch of the CUDA kernels on a lazily created default handle (device 0):
+ *          noise_atap   Src/Speech_Recog/VAD.H:24   (VAD.C:22-71)
+ *          VAD          Src/Speech_Recog/VAD.H:25   (VAD.C:97-218)
+ *          get_mfcc     Src/Speech_Recog/MFCC.H:27  (MFCC.C:86-191)
+ *          dtw          Src/Speech_Recog/DTW.H:7    (DTW.C:120-192)
+ *          fft          Src/Speech_Recog/MFCC.C:27  (global, no header)
+ *          get_dis      Src/Speech_Recog/DTW.C:45   (global, no header)
+ *      A host program written against VAD.H / MFCC.H / DTW.H links unchanged (see include/compat/).
+ *
+ *  (2) Batched, re-entrant forms on an explicit handle (sr_*): B independent utterances per call,
+ *      segments as sample OFFSETS instead of pointers (SR_SEG_NULL = NULL), template bank in the
+ *      reference's flash-slot layout (Src/BSP/Flash.H:11-20). Host-buffer variants copy
+ *      host->device, launch, copy back and synchronise; *_dev variants take device pointers and
+ *      are asynchronous on the handle's stream (sr_set_stream / sr_sync).
+ *
+ * Results are bit-identical to the reference C compiled for a host CPU (VAD boundaries, MFCC
+ * s16, DTW u32 distances, best-template index). There is no CPU fallback: without a CUDA
+ * device every compute entry point fails (sr_* return non-zero; the reference-named functions
+ * write their failure sentinels and set sr_last_error).
+ */
+#ifndef SPEECH_RECOG_H_
+#define SPEECH_RECOG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants visible through the ABI (same values as the reference's macros) ------------- */
+#define SR_FS            8000u        /* ADC.H:7   fs                                   */
+#define SR_VCBUF_LEN     16000u       /* ADC.H:9   VcBuf_Len (2 s)                      */
+#define SR_ATAP_LEN      2400u        /* ADC.H:11  atap_len (300 ms noise window)       */
+#define SR_MAX_VC_CON    3u           /* VAD.H:4   max_vc_con                           */
+#define SR_FRAME_LEN     160u         /* VAD.H:7   frame_len (20 ms)                    */
+#define SR_FRAME_MOV     80u          /* VAD.H:8   frame_mov (10 ms hop)                */
+#define SR_FFT_POINT     1024u        /* MFCC.H:8  fft_point                            */
+#define SR_FRQ_MAX       512u         /* MFCC.H:9  frq_max                              */
+#define SR_TRI_NUM       24u          /* MFCC.H:12 tri_num                              */
+#define SR_MFCC_NUM      12u          /* MFCC.H:13 mfcc_num                             */
+#define SR_VV_FRM_MAX    119u         /* MFCC.H:15-16 vv_frm_max                        */
+#define SR_DIS_ERR       0xFFFFFFFFu  /* DTW.H:4   dis_err                              */
+#define SR_DIS_MAX       0xFFFFFFFFu  /* DTW.H:5   dis_max                              */
+#define SR_SAVE_MASK     12345u       /* Flash.H:11 save_mask                           */
+#define SR_SIZE_PER_FTR  4096u        /* Flash.H:13 size_per_ftr (flash slot)           */
+#define SR_FTR_PER_COMM  4u           /* Flash.H:15 ftr_per_comm                        */
+#define SR_COMM_NUM      20u          /* Flash.H:17 comm_num                            */
+#define SR_SEG_NULL      0xFFFFFFFFu  /* offset encoding of a NULL valid_tag pointer    */
+
+/* per-utterance status of sr_recognise_* (main.c:38-41: save_ok / VAD_fail / MFCC_fail)       */
+#define SR_ST_OK         0u
+#define SR_ST_VAD_FAIL   1u
+#define SR_ST_MFCC_FAIL  2u
+
+/* ---- the reference's types (VAD.H:10-22, MFCC.H:18-25), identical layout -------------------- */
+#ifndef SR_NO_REFERENCE_TYPES
+typedef struct {
+    uint32_t mid_val;   /* DC level of the capture ("signed zero")           */
+    uint16_t n_thl;     /* noise band half-width for the band-crossing rate  */
+    uint16_t z_thl;     /* band-crossing-rate threshold                      */
+    uint32_t s_thl;     /* short-time magnitude threshold                    */
+} atap_tag;
+
+typedef struct {
+    uint16_t *start;    /* first sample of the segment (into the caller's PCM buffer) */
+    uint16_t *end;      /* one past the last sample; NULL = segment never closed      */
+} valid_tag;
+
+#pragma pack(push, 1)
+typedef struct {
+    uint16_t save_sign;                                   /* SR_SAVE_MASK marks a valid flash template */
+    uint16_t frm_num;                                     /* number of MFCC frames                     */
+    int16_t  mfcc_dat[SR_VV_FRM_MAX * SR_MFCC_NUM];       /* row-major frame x coefficient             */
+} v_ftr_tag;                                              /* 2860 bytes                                */
+#pragma pack(pop)
+#endif
+
+/* ---- (1) reference-named entry points ------------------------------------------------------- */
+void      noise_atap(const uint16_t *noise, uint16_t n_len, atap_tag *atap);
+void      VAD(const uint16_t *vc, uint16_t buf_len, valid_tag *valid_voice, atap_tag *atap_arg);
+void      get_mfcc(valid_tag *valid, v_ftr_tag *v_ftr, atap_tag *atap_arg);
+uint32_t  dtw(v_ftr_tag *ftr_in, v_ftr_tag *frt_mdl);
+uint32_t *fft(int16_t *dat_buf, uint16_t buf_len);        /* returns a thread-local u32[1024]; [0,512) valid */
+uint32_t  get_dis(int16_t *frm_ftr1, int16_t *frm_ftr2);
+
+/* ---- (2) batched handle API ----------------------------------------------------------------- */
+typedef struct sr_handle sr_handle;
+
+int         sr_create(int device, sr_handle **out);       /* device ordinal; <0 = current device     */
+int         sr_destroy(sr_handle *h);
+int         sr_set_stream(sr_handle *h, void *cuda_stream /* cudaStream_t, NULL = handle's own */);
+int         sr_sync(sr_handle *h);
+const char *sr_last_error(const sr_handle *h /* NULL: last error of the calling thread */);
+int         sr_device_count(void);                        /* 0 when no CUDA device is usable         */
+int         sr_abi_version(void);
+void       *sr_host_alloc(size_t bytes);                  /* pinned host memory for fast H2D/D2H     */
+void        sr_host_free(void *p);
+
+/* Template bank: n_slot slots of slot_stride bytes (>= sizeof(v_ftr_tag), multiple of 4), each
+ * starting with a v_ftr_tag; the flash layout of Flash.H:11-20 is slot_stride = 4096.
+ * sr_set_bank copies host->device; sr_set_bank_dev borrows a device pointer. */
+int sr_set_bank(sr_handle *h, const void *bank, uint32_t n_slot, uint32_t slot_stride);
+int sr_set_bank_dev(sr_handle *h, const void *bank_dev, uint32_t n_slot, uint32_t slot_stride);
+
+/* pcm: B utterances, utterance b at pcm + b*U (u16 samples, 12-bit ADC codes).
+ * noise_atap over the first n_len samples of every utterance (VAD.C:22-71); atap[b] is left
+ * untouched when n_len % 240 != 0 exactly like the reference (VAD.C:33-36). */
+int sr_noise_atap_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
+                        atap_tag *atap /* [B] in/out */);
+/* VAD over the first buf_len (<= U) samples; seg_off[b][k][0/1] = start/end offset of segment k */
+int sr_vad_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t buf_len,
+                 const atap_tag *atap /* [B] */, uint32_t *seg_off /* [B][3][2] */);
+/* get_mfcc of one segment per utterance: seg[b*seg_stride + 0/1] = start/end sample offsets.
+ * Only frm_num and the first frm_num rows of ftr[b] are written (MFCC.C never writes save_sign). */
+int sr_mfcc_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, const uint32_t *seg,
+                  uint32_t seg_stride, const atap_tag *atap /* [B] */, v_ftr_tag *ftr /* [B] */);
+/* dtw of every input against every bank slot. flags bit0: honour save_sign like spch_recg
+ * (main.c:283: slots whose save_sign != 12345 score SR_DIS_ERR). score may be NULL.
+ * best_idx/best_dis follow main.c:276-291 (strict '<', first wins, start 0 / 0xFFFFFFFF). */
+#define SR_DTW_CHECK_SIGN 1u
+#define SR_DTW_BAND       2u          /* use the Sakoe-Chiba banded DP (extension, not in the reference) */
+int sr_dtw_batch(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, int band_r,
+                 uint32_t *score /* [B][n_slot] or NULL */, uint32_t *best_idx /* [B] or NULL */,
+                 uint32_t *best_dis /* [B] or NULL */);
+/* spch_recg (main.c:249-296) for B utterances: noise_atap(first n_len) -> VAD(U) -> get_mfcc(seg 0)
+ * -> dtw against the bank -> argmin -> cmd = idx / SR_FTR_PER_COMM. Any output pointer may be NULL. */
+typedef struct {
+    atap_tag  *atap;       /* [B]            */
+    uint32_t  *seg_off;    /* [B][3][2]      */
+    v_ftr_tag *ftr;        /* [B]            */
+    uint32_t  *score;      /* [B][n_slot]    */
+    uint32_t  *best_idx;   /* [B]            */
+    uint32_t  *best_dis;   /* [B] (mtch_dis) */
+    uint32_t  *cmd;        /* [B]            */
+    uint8_t   *status;     /* [B] SR_ST_*    */
+} sr_recog_out;
+int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
+                       const sr_recog_out *out);
+
+/* device-pointer variants: every pointer is device memory on the handle's device, calls are
+ * asynchronous on the handle's stream. Alignment: pcm 2 bytes, everything else 4 bytes. */
+int sr_noise_atap_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, atap_tag *atap);
+int sr_vad_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t buf_len,
+                     const atap_tag *atap, uint32_t *seg_off);
+int sr_mfcc_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, const uint32_t *seg,
+                      uint32_t seg_stride, const atap_tag *atap, v_ftr_tag *ftr);
+int sr_dtw_batch_dev(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, int band_r,
+                     uint32_t *score, uint32_t *best_idx, uint32_t *best_dis);
+int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
+                           const sr_recog_out *out_dev);
+
+/* secondary globals of the reference, batched: fft magnitudes (MFCC.C:27-62) of n frames of
+ * `len` (<=1024) s16 samples each -> u32[n][512]; get_dis (DTW.C:45-62) of n row pairs. */
+int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t n, uint32_t *mag);
+int sr_get_dis_batch(sr_handle *h, const int16_t *a, const int16_t *b, uint32_t n, uint32_t *dis);
+/* raw cr4_fft_1024_stm32 (Src/BSP/cr4_fft_1024_stm32.s:219-281) of n packed inputs (re | im<<16,
+ * u32[n][1024]) -> packed outputs; exists so tests can pin the FFT kernel code against the asm restatement
+ * on arbitrary complex data */
+int sr_fft_raw_batch(sr_handle *h, const uint32_t *in_packed, uint32_t n, uint32_t *out_packed);
+
+/* number of kernel launches this handle has issued (bench.py reports it as gpu_launches) */
+uint64_t sr_launch_count(const sr_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECH_RECOG_H_ */

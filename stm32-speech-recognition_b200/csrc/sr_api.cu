@@ -1,0 +1,542 @@
+// sr_api.cu -- the C-ABI of libspeech_b200.so (include/speech_recog.h): handle, device workspaces,
+// host<->device plumbing and the reference-named batch-of-1 entry points. No arithmetic of the
+// recognition path happens on the host: every result is produced by the kernels in sr_vad.cu,
+// sr_mfcc.cu and sr_dtw.cu. Without a CUDA device every entry point fails loudly.
+#include <mutex>
+#include <new>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "sr_common.cuh"
+
+namespace srk {
+cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad, atap_tag *atap,
+                       u32 *seg_off, int num_sms, cudaStream_t st);
+cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
+                        int num_sms, cudaStream_t st);
+cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
+                               cudaStream_t st);
+cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st);
+cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, int band_r,
+                            u32 *score, u64 *best, int num_sms, cudaStream_t st);
+cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st);
+cudaError_t launch_best_final(const u64 *best, u32 B, u32 *best_idx, u32 *best_dis, u32 *cmd, const u8 *status,
+                              cudaStream_t st);
+cudaError_t launch_status(const u32 *seg_off, const void *ftr, u32 B, u8 *status, cudaStream_t st);
+cudaError_t launch_get_dis(const s16 *a, const s16 *b, u32 n, u32 *out, cudaStream_t st);
+}  // namespace srk
+
+using namespace srk;
+
+static thread_local std::string g_tls_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct sr_handle {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::string err;
+    // template bank
+    const void *bank = nullptr;
+    DevBuf bank_own;
+    u32 n_slot = 0, slot_stride = 0;
+    // grow-only device workspaces
+    DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
+};
+
+static int fail(sr_handle *h, const char *what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+    g_tls_error = buf;
+    if (h) h->err = buf;
+    return e == cudaSuccess ? -1 : (int)e;
+}
+#define SR_CK(h, call)                                           \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return fail((h), #call, e__);    \
+    } while (0)
+#define SR_REQUIRE(h, cond)                                      \
+    do {                                                         \
+        if (!(cond)) return fail((h), "requirement failed: " #cond, cudaSuccess); \
+    } while (0)
+
+static cudaError_t ensure(DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return cudaSuccess;
+    if (b.p) { cudaError_t e = cudaFree(b.p); b.p = nullptr; b.cap = 0; if (e != cudaSuccess) return e; }
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { b.p = nullptr; return e; }
+    b.cap = want;
+    return cudaSuccess;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" {
+
+int sr_abi_version(void) { return 1; }
+
+int sr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *sr_last_error(const sr_handle *h) { return h ? h->err.c_str() : g_tls_error.c_str(); }
+
+int sr_create(int device, sr_handle **out) {
+    if (!out) return fail(nullptr, "sr_create: out == NULL", cudaSuccess);
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, "sr_create: no CUDA device (libspeech_b200 has no CPU fallback)", e == cudaSuccess ? cudaErrorNoDevice : e);
+    if (device < 0) SR_CK(nullptr, cudaGetDevice(&device));
+    if (device >= n) return fail(nullptr, "sr_create: device ordinal out of range", cudaErrorInvalidDevice);
+    sr_handle *h = new (std::nothrow) sr_handle;
+    if (!h) return fail(nullptr, "sr_create: out of host memory", cudaErrorMemoryAllocation);
+    h->device = device;
+    DeviceGuard g(device);
+    if (!g.ok) { delete h; return fail(nullptr, "sr_create: cudaSetDevice", cudaErrorInvalidDevice); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, "cudaGetDeviceProperties", e); }
+    if (prop.major < 10) {
+        delete h;
+        return fail(nullptr, "sr_create: kernels are built for sm_100a (B200) only", cudaErrorInvalidDevice);
+    }
+    h->num_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, "cudaStreamCreate", e); }
+    h->stream = h->own_stream;
+    if (!dev_tables()) { cudaStreamDestroy(h->own_stream); delete h; return fail(nullptr, "table upload", cudaErrorInitializationError); }
+    *out = h;
+    return 0;
+}
+
+int sr_destroy(sr_handle *h) {
+    if (!h) return 0;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
+                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int sr_set_stream(sr_handle *h, void *cuda_stream) {
+    SR_REQUIRE(h, h != nullptr);
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return 0;
+}
+
+int sr_sync(sr_handle *h) {
+    SR_REQUIRE(h, h != nullptr);
+    DeviceGuard g(h->device);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+uint64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
+
+void *sr_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void sr_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- template bank --------------------------------------------------------------------------------
+int sr_set_bank_dev(sr_handle *h, const void *bank_dev, uint32_t n_slot, uint32_t slot_stride) {
+    SR_REQUIRE(h, h != nullptr);
+    SR_REQUIRE(h, n_slot == 0 || (bank_dev != nullptr && slot_stride >= (uint32_t)kFtrBytes && slot_stride % 4 == 0));
+    SR_REQUIRE(h, (reinterpret_cast<uintptr_t>(bank_dev) & 3) == 0);
+    h->bank = bank_dev; h->n_slot = n_slot; h->slot_stride = slot_stride;
+    return 0;
+}
+int sr_set_bank(sr_handle *h, const void *bank, uint32_t n_slot, uint32_t slot_stride) {
+    SR_REQUIRE(h, h != nullptr);
+    SR_REQUIRE(h, n_slot == 0 || (bank != nullptr && slot_stride >= (uint32_t)kFtrBytes && slot_stride % 4 == 0));
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)n_slot * slot_stride;
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    SR_CK(h, ensure(h->bank_own, bytes + 16));
+    if (bytes) SR_CK(h, cudaMemcpyAsync(h->bank_own.p, bank, bytes, cudaMemcpyHostToDevice, h->stream));
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    h->bank = h->bank_own.p; h->n_slot = n_slot; h->slot_stride = slot_stride;
+    return 0;
+}
+
+// ---- device-pointer entry points ------------------------------------------------------------------
+int sr_noise_atap_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, atap_tag *atap) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && atap)));
+    SR_REQUIRE(h, U <= 65535u && n_len <= 65535u);
+    DeviceGuard g(h->device);
+    SR_CK(h, launch_vad(pcm, U, B, n_len, 0, 1, 0, atap, nullptr, h->num_sms, h->stream));
+    h->launches += B ? 1 : 0;
+    return 0;
+}
+
+int sr_vad_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t buf_len, const atap_tag *atap,
+                     uint32_t *seg_off) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && atap && seg_off)));
+    SR_REQUIRE(h, U <= 65535u && buf_len <= U);
+    DeviceGuard g(h->device);
+    SR_CK(h, launch_vad(pcm, U, B, 0, buf_len, 0, 1, const_cast<atap_tag *>(atap), seg_off, h->num_sms, h->stream));
+    h->launches += B ? 1 : 0;
+    return 0;
+}
+
+int sr_mfcc_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, const uint32_t *seg, uint32_t seg_stride,
+                      const atap_tag *atap, v_ftr_tag *ftr) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && seg && atap && ftr)));
+    SR_REQUIRE(h, seg_stride >= 2 && (reinterpret_cast<uintptr_t>(ftr) & 3) == 0);
+    DeviceGuard g(h->device);
+    SR_CK(h, launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream));
+    h->launches += B ? 1 : 0;
+    return 0;
+}
+
+static int dtw_dev_impl(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, int band_r, uint32_t *score,
+                        uint32_t *best_idx, uint32_t *best_dis, uint32_t *cmd, const u8 *status) {
+    SR_REQUIRE(h, h && (B == 0 || in));
+    SR_REQUIRE(h, (reinterpret_cast<uintptr_t>(in) & 3) == 0);
+    if (B == 0) return 0;
+    const bool want_best = best_idx || best_dis || cmd;
+    u64 *best = nullptr;
+    if (want_best) {
+        SR_CK(h, ensure(h->best, (size_t)B * 8));
+        best = static_cast<u64 *>(h->best.p);
+        SR_CK(h, launch_best_init(best, B, h->stream));
+        ++h->launches;
+    }
+    if (h->n_slot) {
+        if (flags & SR_DTW_BAND) {
+            SR_REQUIRE(h, band_r >= 0);
+            SR_CK(h, launch_dtw_band(in, B, h->bank, h->n_slot, h->slot_stride, flags, band_r, score, best, h->num_sms, h->stream));
+        } else {
+            SR_CK(h, launch_dtw(in, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream));
+        }
+        ++h->launches;
+    }
+    if (want_best) {
+        SR_CK(h, launch_best_final(best, B, best_idx, best_dis, cmd, status, h->stream));
+        ++h->launches;
+    }
+    return 0;
+}
+
+int sr_dtw_batch_dev(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, int band_r, uint32_t *score,
+                     uint32_t *best_idx, uint32_t *best_dis) {
+    SR_REQUIRE(h, h != nullptr);
+    DeviceGuard g(h->device);
+    return dtw_dev_impl(h, in, B, flags, band_r, score, best_idx, best_dis, nullptr, nullptr);
+}
+
+int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
+                           const sr_recog_out *o) {
+    SR_REQUIRE(h, h && o && (B == 0 || pcm));
+    SR_REQUIRE(h, U <= 65535u && n_len <= U);
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    atap_tag *atap = o->atap;
+    if (!atap) {
+        SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag)));
+        atap = static_cast<atap_tag *>(h->atap.p);
+        SR_CK(h, cudaMemsetAsync(atap, 0, (size_t)B * sizeof(atap_tag), h->stream));
+    }
+    u32 *seg = o->seg_off;
+    if (!seg) { SR_CK(h, ensure(h->seg, (size_t)B * 24)); seg = static_cast<u32 *>(h->seg.p); }
+    v_ftr_tag *ftr = o->ftr;
+    if (!ftr) { SR_CK(h, ensure(h->ftr, (size_t)B * kFtrBytes)); ftr = static_cast<v_ftr_tag *>(h->ftr.p); }
+    u8 *status = o->status;
+    if (!status) { SR_CK(h, ensure(h->status, (size_t)B)); status = static_cast<u8 *>(h->status.p); }
+    // main.c:258-260 noise_atap + VAD (one fused launch on the staged utterance)
+    SR_CK(h, launch_vad(pcm, U, B, n_len, U, 1, 1, atap, seg, h->num_sms, h->stream));
+    // main.c:268 get_mfcc of segment 0
+    SR_CK(h, launch_mfcc(pcm, U, B, seg, 6, atap, ftr, h->num_sms, h->stream));
+    SR_CK(h, launch_status(seg, ftr, B, status, h->stream));
+    h->launches += 3;
+    // main.c:276-294 template scan, argmin, command index
+    return dtw_dev_impl(h, ftr, B, SR_DTW_CHECK_SIGN, 0, o->score, o->best_idx, o->best_dis, o->cmd, status);
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------
+#define H2D(h, dst, src, bytes) SR_CK(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (h)->stream))
+#define D2H(h, dst, src, bytes) SR_CK(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (h)->stream))
+
+int sr_noise_atap_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, atap_tag *atap) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && atap)));
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));
+    SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag)));
+    H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
+    H2D(h, h->atap.p, atap, (size_t)B * sizeof(atap_tag));
+    int rc = sr_noise_atap_batch_dev(h, static_cast<const u16 *>(h->pcm.p), U, B, n_len, static_cast<atap_tag *>(h->atap.p));
+    if (rc) return rc;
+    D2H(h, atap, h->atap.p, (size_t)B * sizeof(atap_tag));
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sr_vad_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t buf_len, const atap_tag *atap,
+                 uint32_t *seg_off) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && atap && seg_off)));
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));
+    SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag)));
+    SR_CK(h, ensure(h->seg, (size_t)B * 24));
+    H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
+    H2D(h, h->atap.p, atap, (size_t)B * sizeof(atap_tag));
+    int rc = sr_vad_batch_dev(h, static_cast<const u16 *>(h->pcm.p), U, B, buf_len, static_cast<const atap_tag *>(h->atap.p),
+                              static_cast<u32 *>(h->seg.p));
+    if (rc) return rc;
+    D2H(h, seg_off, h->seg.p, (size_t)B * 24);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sr_mfcc_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, const uint32_t *seg, uint32_t seg_stride,
+                  const atap_tag *atap, v_ftr_tag *ftr) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && seg && atap && ftr)));
+    SR_REQUIRE(h, seg_stride >= 2);
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));
+    SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag)));
+    SR_CK(h, ensure(h->seg, (size_t)B * seg_stride * 4));
+    SR_CK(h, ensure(h->ftr, (size_t)B * kFtrBytes));
+    H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
+    H2D(h, h->atap.p, atap, (size_t)B * sizeof(atap_tag));
+    H2D(h, h->seg.p, seg, (size_t)B * seg_stride * 4);
+    int rc = sr_mfcc_batch_dev(h, static_cast<const u16 *>(h->pcm.p), U, B, static_cast<const u32 *>(h->seg.p), seg_stride,
+                               static_cast<const atap_tag *>(h->atap.p), static_cast<v_ftr_tag *>(h->ftr.p));
+    if (rc) return rc;
+    // MFCC.C never writes save_sign: copy back bytes [2, 2860) of every struct only
+    SR_CK(h, cudaMemcpy2DAsync(reinterpret_cast<unsigned char *>(ftr) + 2, kFtrBytes,
+                               static_cast<unsigned char *>(h->ftr.p) + 2, kFtrBytes, kFtrBytes - 2, B,
+                               cudaMemcpyDeviceToHost, h->stream));
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sr_dtw_batch(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, int band_r, uint32_t *score,
+                 uint32_t *best_idx, uint32_t *best_dis) {
+    SR_REQUIRE(h, h && (B == 0 || in));
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    const size_t T = h->n_slot;
+    SR_CK(h, ensure(h->ftr, (size_t)B * kFtrBytes));
+    if (score) SR_CK(h, ensure(h->score, (size_t)B * T * 4 + 4));
+    SR_CK(h, ensure(h->bidx, (size_t)B * 4));
+    SR_CK(h, ensure(h->bdis, (size_t)B * 4));
+    H2D(h, h->ftr.p, in, (size_t)B * kFtrBytes);
+    int rc = dtw_dev_impl(h, static_cast<const v_ftr_tag *>(h->ftr.p), B, flags, band_r,
+                          score ? static_cast<u32 *>(h->score.p) : nullptr,
+                          best_idx ? static_cast<u32 *>(h->bidx.p) : nullptr,
+                          best_dis ? static_cast<u32 *>(h->bdis.p) : nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (score && T) D2H(h, score, h->score.p, (size_t)B * T * 4);
+    if (best_idx) D2H(h, best_idx, h->bidx.p, (size_t)B * 4);
+    if (best_dis) D2H(h, best_dis, h->bdis.p, (size_t)B * 4);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, const sr_recog_out *o) {
+    SR_REQUIRE(h, h && o && (B == 0 || pcm));
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    const size_t T = h->n_slot;
+    SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));
+    H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
+    sr_recog_out d;
+    memset(&d, 0, sizeof d);
+    if (o->atap) { SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag))); d.atap = static_cast<atap_tag *>(h->atap.p);
+                   H2D(h, d.atap, o->atap, (size_t)B * sizeof(atap_tag)); }
+    if (o->seg_off) { SR_CK(h, ensure(h->seg, (size_t)B * 24)); d.seg_off = static_cast<u32 *>(h->seg.p); }
+    if (o->ftr) { SR_CK(h, ensure(h->ftr, (size_t)B * kFtrBytes)); d.ftr = static_cast<v_ftr_tag *>(h->ftr.p); }
+    if (o->score) { SR_CK(h, ensure(h->score, (size_t)B * T * 4 + 4)); d.score = static_cast<u32 *>(h->score.p); }
+    if (o->best_idx) { SR_CK(h, ensure(h->bidx, (size_t)B * 4)); d.best_idx = static_cast<u32 *>(h->bidx.p); }
+    if (o->best_dis) { SR_CK(h, ensure(h->bdis, (size_t)B * 4)); d.best_dis = static_cast<u32 *>(h->bdis.p); }
+    if (o->cmd) { SR_CK(h, ensure(h->cmd, (size_t)B * 4)); d.cmd = static_cast<u32 *>(h->cmd.p); }
+    if (o->status) { SR_CK(h, ensure(h->status, (size_t)B)); d.status = static_cast<u8 *>(h->status.p); }
+    int rc = sr_recognise_batch_dev(h, static_cast<const u16 *>(h->pcm.p), U, B, n_len, &d);
+    if (rc) return rc;
+    if (o->atap) D2H(h, o->atap, d.atap, (size_t)B * sizeof(atap_tag));
+    if (o->seg_off) D2H(h, o->seg_off, d.seg_off, (size_t)B * 24);
+    if (o->ftr)
+        SR_CK(h, cudaMemcpy2DAsync(reinterpret_cast<unsigned char *>(o->ftr) + 2, kFtrBytes,
+                                   reinterpret_cast<unsigned char *>(d.ftr) + 2, kFtrBytes, kFtrBytes - 2, B,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    if (o->score && T) D2H(h, o->score, d.score, (size_t)B * T * 4);
+    if (o->best_idx) D2H(h, o->best_idx, d.best_idx, (size_t)B * 4);
+    if (o->best_dis) D2H(h, o->best_dis, d.best_dis, (size_t)B * 4);
+    if (o->cmd) D2H(h, o->cmd, d.cmd, (size_t)B * 4);
+    if (o->status) D2H(h, o->status, d.status, (size_t)B);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t n, uint32_t *mag) {
+    SR_REQUIRE(h, h && (n == 0 || (frames && mag)));
+    SR_REQUIRE(h, len <= SR_FFT_POINT);                                   // MFCC.C:32-35
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->misc0, (size_t)n * len * 2 + 16));
+    SR_CK(h, ensure(h->misc1, (size_t)n * 512 * 4));
+    if (len) H2D(h, h->misc0.p, frames, (size_t)n * len * 2);
+    SR_CK(h, launch_fft_generic(nullptr, static_cast<const s16 *>(h->misc0.p), len, n, nullptr, static_cast<u32 *>(h->misc1.p), h->stream));
+    ++h->launches;
+    D2H(h, mag, h->misc1.p, (size_t)n * 512 * 4);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// raw FFT of packed (re | im<<16) 1024-point inputs -- test hook for the asm restatement parity
+int sr_fft_raw_batch(sr_handle *h, const uint32_t *in_packed, uint32_t n, uint32_t *out_packed) {
+    SR_REQUIRE(h, h && (n == 0 || (in_packed && out_packed)));
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->misc0, (size_t)n * 4096));
+    SR_CK(h, ensure(h->misc1, (size_t)n * 4096));
+    H2D(h, h->misc0.p, in_packed, (size_t)n * 4096);
+    SR_CK(h, launch_fft_generic(static_cast<const u32 *>(h->misc0.p), nullptr, 0, n, static_cast<u32 *>(h->misc1.p), nullptr, h->stream));
+    ++h->launches;
+    D2H(h, out_packed, h->misc1.p, (size_t)n * 4096);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sr_get_dis_batch(sr_handle *h, const int16_t *a, const int16_t *b, uint32_t n, uint32_t *dis) {
+    SR_REQUIRE(h, h && (n == 0 || (a && b && dis)));
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->misc0, (size_t)n * 24));
+    SR_CK(h, ensure(h->misc1, (size_t)n * 24));
+    SR_CK(h, ensure(h->misc2, (size_t)n * 4));
+    H2D(h, h->misc0.p, a, (size_t)n * 24);
+    H2D(h, h->misc1.p, b, (size_t)n * 24);
+    SR_CK(h, launch_get_dis(static_cast<const s16 *>(h->misc0.p), static_cast<const s16 *>(h->misc1.p), n, static_cast<u32 *>(h->misc2.p), h->stream));
+    ++h->launches;
+    D2H(h, dis, h->misc2.p, (size_t)n * 4);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- (1) the reference's own entry points: batch-of-1 on a lazily created default handle -----------
+static std::mutex g_default_mu;
+static sr_handle *g_default = nullptr;
+static sr_handle *default_handle() {
+    if (!g_default) {
+        sr_handle *h = nullptr;
+        if (sr_create(0, &h) == 0) g_default = h;
+    }
+    return g_default;
+}
+
+// VAD.H:24 / VAD.C:22-71. On failure (no device) *atap is left untouched and sr_last_error(NULL) is set.
+void noise_atap(const uint16_t *noise, uint16_t n_len, atap_tag *atap) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    if (!h || !noise || !atap) return;
+    if (n_len == 0) return;
+    sr_noise_atap_batch(h, noise, n_len, 1, n_len, atap);
+}
+
+// VAD.H:25 / VAD.C:97-218. Segments come back as pointers into the caller's buffer.
+void VAD(const uint16_t *vc, uint16_t buf_len, valid_tag *valid_voice, atap_tag *atap_arg) {
+    if (valid_voice) for (unsigned i = 0; i < SR_MAX_VC_CON; ++i) { valid_voice[i].start = nullptr; valid_voice[i].end = nullptr; }   // VAD.C:115-119
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    if (!h || !vc || !valid_voice || !atap_arg || buf_len == 0) return;
+    uint32_t seg[6];
+    if (sr_vad_batch(h, vc, buf_len, 1, buf_len, atap_arg, seg) != 0) return;
+    for (unsigned i = 0; i < SR_MAX_VC_CON; ++i) {
+        valid_voice[i].start = seg[2 * i] == SR_SEG_NULL ? nullptr : const_cast<uint16_t *>(vc) + seg[2 * i];
+        valid_voice[i].end = seg[2 * i + 1] == SR_SEG_NULL ? nullptr : const_cast<uint16_t *>(vc) + seg[2 * i + 1];
+    }
+}
+
+// MFCC.H:27 / MFCC.C:86-191. Like the reference this reads valid->start[-1] (MFCC.C:119, i=0).
+void get_mfcc(valid_tag *valid, v_ftr_tag *v_ftr, atap_tag *atap_arg) {
+    if (!v_ftr) return;
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    if (!h || !valid || !atap_arg || !valid->start || !valid->end || valid->end < valid->start) { v_ftr->frm_num = 0; return; }
+    size_t len = (size_t)(valid->end - valid->start);
+    // more than vv_frm_max frames is rejected by the kernel (MFCC.C:103-107); cap what is shipped to the device
+    const size_t cap = 120 * 80 + 80;
+    if (len > cap) len = cap;
+    const uint32_t U = (uint32_t)len + 1;
+    const uint32_t seg[2] = {1u, U};
+    if (sr_mfcc_batch(h, valid->start - 1, U, 1, seg, 2, atap_arg, v_ftr) != 0) v_ftr->frm_num = 0;
+}
+
+// DTW.H:7 / DTW.C:120-192
+uint32_t dtw(v_ftr_tag *ftr_in, v_ftr_tag *frt_mdl) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    if (!h || !ftr_in || !frt_mdl) return SR_DIS_ERR;
+    const void *sv_bank = h->bank; const u32 sv_n = h->n_slot, sv_s = h->slot_stride;
+    uint32_t score = SR_DIS_ERR;
+    DeviceGuard g(h->device);
+    if (ensure(h->misc2, kFtrBytes + 16) != cudaSuccess) return SR_DIS_ERR;
+    if (cudaMemcpyAsync(h->misc2.p, frt_mdl, kFtrBytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return SR_DIS_ERR;
+    h->bank = h->misc2.p; h->n_slot = 1; h->slot_stride = kFtrBytes;
+    const int rc = sr_dtw_batch(h, ftr_in, 1, 0, 0, &score, nullptr, nullptr);
+    h->bank = sv_bank; h->n_slot = sv_n; h->slot_stride = sv_s;
+    return rc == 0 ? score : SR_DIS_ERR;
+}
+
+// MFCC.C:27-62: returns a pointer to a buffer owned by the library (thread-local instead of the
+// reference's single static): [0,512) magnitudes, [512,1024) the raw packed FFT bins like fft_out.
+uint32_t *fft(int16_t *dat_buf, uint16_t buf_len) {
+    static thread_local uint32_t out[SR_FFT_POINT];
+    if (buf_len > SR_FFT_POINT || !dat_buf) return nullptr;          // MFCC.C:32-35
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    if (!h) return nullptr;
+    DeviceGuard g(h->device);
+    if (ensure(h->misc0, 4096) != cudaSuccess || ensure(h->misc1, 4096) != cudaSuccess || ensure(h->misc2, 2048) != cudaSuccess) return nullptr;
+    if (buf_len && cudaMemcpyAsync(h->misc0.p, dat_buf, (size_t)buf_len * 2, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return nullptr;
+    if (launch_fft_generic(nullptr, static_cast<const s16 *>(h->misc0.p), buf_len, 1, static_cast<u32 *>(h->misc1.p),
+                           static_cast<u32 *>(h->misc2.p), h->stream) != cudaSuccess) return nullptr;
+    ++h->launches;
+    if (cudaMemcpyAsync(out, h->misc2.p, 2048, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return nullptr;
+    if (cudaMemcpyAsync(out + 512, static_cast<u32 *>(h->misc1.p) + 512, 2048, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return nullptr;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return nullptr;
+    return out;
+}
+
+// DTW.C:45-62
+uint32_t get_dis(int16_t *frm_ftr1, int16_t *frm_ftr2) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    if (!h || !frm_ftr1 || !frm_ftr2) return SR_DIS_ERR;
+    uint32_t d = SR_DIS_ERR;
+    if (sr_get_dis_batch(h, frm_ftr1, frm_ftr2, 1, &d) != 0) return SR_DIS_ERR;
+    return d;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// sr_dtw.cu -- K2: batched dtw (Src/Speech_Recog/DTW.C:120-192) = the reference's GREEDY walk through
+// the slope-2 / slope-1/2 parallelogram (dtw_limit, DTW.C:76-109) with the 12-dim integer local
+// distance get_dis (DTW.C:45-62), plus the spch_recg argmin (Src/APP/main.c:276-291) as an epilogue.
+//
+// Mapping: one thread per (utterance, template) pair -- the walk is inherently sequential and
+// data dependent; parallelism is across the B x T pairs. A CTA keeps a tile of 32 templates in
+// shared memory (loaded once, reused for every utterance the CTA visits) and each of its 16 warps
+// walks one utterance against those 32 templates (lane = template), the utterance's rows staged
+// in shared memory too. Local distances use  sum (a-b)^2 = |a|^2 + |b|^2 - 2 a.b  (exact in the
+// ring Z/2^32 in which the reference accumulates), with |row|^2 precomputed per staged row.
+#include "sr_common.cuh"
+
+namespace srk {
+
+constexpr int kDtwWarps = 16;
+constexpr int kTileT = 32;
+constexpr int kRowsBytes = 119 * 24;        // 2856
+
+struct __align__(16) DtwSmem {
+    unsigned char trow[kTileT][kRowsBytes];   // template rows (s16[119][12])
+    unsigned char urow[kDtwWarps][kRowsBytes];
+    u32 tnorm[kTileT][120];
+    u32 unorm[kDtwWarps][120];
+    u32 tfrm[kTileT];                         // frm_num, or 0xFFFFFFFF = slot does not take part
+};
+
+struct Row { s32 v[12]; };
+
+__device__ __forceinline__ void load_row(Row &r, const unsigned char *rows, int idx) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(rows + idx * 24);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint2 q = p[j];
+        r.v[4 * j + 0] = (s32)lo16s(q.x); r.v[4 * j + 1] = (s32)hi16s(q.x);
+        r.v[4 * j + 2] = (s32)lo16s(q.y); r.v[4 * j + 3] = (s32)hi16s(q.y);
+    }
+}
+__device__ __forceinline__ u32 dot12(const Row &a, const Row &b) {
+    u32 s = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s += (u32)a.v[j] * (u32)b.v[j];
+    return s;
+}
+// get_dis, DTW.C:45-62, from the precomputed squared norms
+__device__ __forceinline__ u32 dist(const Row &a, u32 na, const Row &b, u32 nb) {
+    return usqrt_trunc(na + nb - 2u * dot12(a, b));
+}
+// dtw_limit, DTW.C:76-109: true = "ins"
+__device__ __forceinline__ bool inside(int x, int y, int X1, int X2, int I, int M) {
+    x &= 0xFFFF; y &= 0xFFFF;
+    const bool out_a = (x < X1) ? (y >= 2 * x + 2) : (2 * y + I - 2 * M >= x + 4);
+    const bool out_b = (x < X2) ? (2 * y + 2 <= x) : (y + 4 <= 2 * x + M - 2 * I);
+    return !(out_a || out_b);
+}
+
+__device__ __forceinline__ void stage_rows(unsigned char *dst, u32 *norm, const unsigned char *src_ftr, int nrows,
+                                           int lane, int nlanes) {
+    // src_ftr points at a v_ftr_tag (4-byte aligned); rows start at +4
+    const u32 *s = reinterpret_cast<const u32 *>(src_ftr + 4);
+    u32 *d = reinterpret_cast<u32 *>(dst);
+    for (int i = lane; i < nrows * 6; i += nlanes) d[i] = s[i];
+}
+__device__ __forceinline__ void row_norms(const unsigned char *rows, u32 *norm, int nrows, int lane, int nlanes) {
+    for (int r = lane; r < nrows; r += nlanes) {
+        Row t; load_row(t, rows, r);
+        norm[r] = dot12(t, t);
+    }
+}
+
+__global__ void __launch_bounds__(kDtwWarps * 32)
+dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
+           u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best,
+           const u8 *__restrict__ status /* may be NULL: per-utterance SR_ST_* gate of sr_recognise */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DtwSmem &sm = *reinterpret_cast<DtwSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 t0 = blockIdx.x * kTileT;
+
+    // ---- template tile: rows + norms + frame counts ---------------------------------------------
+    for (int tt = warp; tt < kTileT; tt += kDtwWarps) {
+        const u32 t = t0 + tt;
+        u32 frm = 0xFFFFFFFFu;
+        if (t < T) {
+            const unsigned char *slot = bank + (size_t)t * slot_stride;
+            const u32 hdr = *reinterpret_cast<const u32 *>(slot);
+            const u32 sign = hdr & 0xFFFFu;
+            frm = hdr >> 16;
+            if ((flags & SR_DTW_CHECK_SIGN) && sign != SR_SAVE_MASK) frm = 0xFFFFFFFFu;   // main.c:283
+            const int nrows = (frm == 0xFFFFFFFFu) ? 0 : (int)min(frm + 1u, 119u);        // +1: the do-while may touch row frm
+            stage_rows(sm.trow[tt], sm.tnorm[tt], slot, nrows, lane, 32);
+            __syncwarp();
+            row_norms(sm.trow[tt], sm.tnorm[tt], nrows, lane, 32);
+        }
+        if (lane == 0) sm.tfrm[tt] = frm;
+    }
+    __syncthreads();
+
+    const u32 t = t0 + lane;
+    const u32 Mraw = sm.tfrm[lane];
+    const unsigned char *trow = sm.trow[lane];
+    const u32 *tnorm = sm.tnorm[lane];
+    unsigned char *urow = sm.urow[warp];
+    u32 *unorm = sm.unorm[warp];
+
+    for (u32 u = blockIdx.y * kDtwWarps + warp; u < B; u += gridDim.y * kDtwWarps) {
+        const unsigned char *uf = in_ftr + (size_t)u * kFtrBytes;
+        const u32 Iraw = (*reinterpret_cast<const u32 *>(uf)) >> 16;
+        const bool gated = status && status[u] != SR_ST_OK;          // VAD/MFCC failed: spch_recg returns before dtw
+        __syncwarp();
+        if (!gated) {
+            const int nrows = (int)min(Iraw + 1u, 119u);
+            stage_rows(urow, unorm, uf, nrows, lane, 32);
+            __syncwarp();
+            row_norms(urow, unorm, nrows, lane, 32);
+        }
+        __syncwarp();
+
+        u32 result = SR_DIS_ERR;
+        const int I = (int)Iraw, M = (int)Mraw;
+        bool walk = !gated && t < T && Mraw != 0xFFFFFFFFu && !(I > M * 2 || 2 * I < M) && I <= 119 && M <= 119;   // DTW.C:133
+        if (walk) {
+            const int X1 = (2 * M - I) / 3, X2 = (4 * I - 2 * M) / 3;            // DTW.C:141-142
+            Row i0, i1, m0, m1;
+            load_row(i0, urow, 0); load_row(m0, trow, 0);
+            load_row(i1, urow, 1); load_row(m1, trow, 1);
+            u32 ni0 = unorm[0], ni1 = unorm[1], nm0 = tnorm[0], nm1 = tnorm[1];
+            u32 dis = dist(i0, ni0, m0, nm0);                                      // DTW.C:146
+            int x = 1, y = 1;
+            u32 step = 1;
+            do {                                                                   // DTW.C:150-188
+                const u32 up = inside(x, y + 1, X1, X2, I, M) ? dist(m1, nm1, i0, ni0) : SR_DIS_ERR;
+                const u32 right = inside(x + 1, y, X1, X2, I, M) ? dist(m0, nm0, i1, ni1) : SR_DIS_ERR;
+                const u32 ru = inside(x + 1, y + 1, X1, X2, I, M) ? dist(m1, nm1, i1, ni1) : SR_DIS_ERR;
+                u32 mn = ru;
+                if (mn > right) mn = right;
+                if (mn > up) mn = up;
+                dis += mn;
+                const bool mv_x = (mn == ru) || (mn != up);                         // diag, else up, else right
+                const bool mv_y = (mn == ru) || (mn == up);
+                if (mv_x) { i0 = i1; ni0 = ni1; ++x; }
+                if (mv_y) { m0 = m1; nm0 = nm1; ++y; }
+                ++step;
+                const bool more = (x < I) && (y < M);
+                if (more) {
+                    if (mv_x) { load_row(i1, urow, x); ni1 = unorm[x]; }
+                    if (mv_y) { load_row(m1, trow, y); nm1 = tnorm[y]; }
+                } else break;
+            } while (true);
+            result = dis / (step & 0xFFFFu);                                       // DTW.C:191 (step is u16)
+        }
+        if (t < T && score) score[(size_t)u * T + t] = result;
+        if (best) {                                                                // uniform branch: all 32 lanes shuffle
+            u64 key = t < T ? (((u64)result << 32) | (u64)t) : ~0ull;              // strict '<', first wins == lexicographic min
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const u64 other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                key = other < key ? other : key;
+            }
+            if (lane == 0) atomicMin(reinterpret_cast<unsigned long long *>(&best[u]), (unsigned long long)key);
+        }
+    }
+}
+
+// best[] initialiser and finaliser (main.c:276-278 min_comm=0, min_dis=dis_max; main.c:292-294)
+__global__ void best_init_kernel(u64 *best, u32 B) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) best[i] = ((u64)SR_DIS_MAX << 32) | 0ull;
+}
+__global__ void best_final_kernel(const u64 *best, u32 B, u32 *best_idx, u32 *best_dis, u32 *cmd, const u8 *status) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    u64 k = best[i];
+    u32 idx = (u32)(k & 0xFFFFFFFFull), dis = (u32)(k >> 32);
+    if (status && status[i] != SR_ST_OK) { idx = 0; dis = SR_DIS_ERR; }            // main.c:261-274
+    if (best_idx) best_idx[i] = idx;
+    if (best_dis) best_dis[i] = dis;
+    if (cmd) cmd[i] = idx / SR_FTR_PER_COMM;
+}
+
+// status of the recognise pipeline from VAD/MFCC results (main.c:261-274)
+__global__ void status_kernel(const u32 *seg_off, const unsigned char *ftr, u32 B, u8 *status) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    u8 st = SR_ST_OK;
+    if (seg_off[(size_t)i * 6 + 1] == SR_SEG_NULL) st = SR_ST_VAD_FAIL;
+    else if (((*reinterpret_cast<const u32 *>(ftr + (size_t)i * kFtrBytes)) >> 16) == 0) st = SR_ST_MFCC_FAIL;
+    status[i] = st;
+}
+
+// get_dis for n independent row pairs (secondary drop-in symbol, DTW.C:45-62)
+__global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 d = 0;
+    for (int j = 0; j < 12; ++j) {
+        const s32 dif = (s32)a[(size_t)i * 12 + j] - (s32)b[(size_t)i * 12 + j];
+        d += (u32)dif * (u32)dif;
+    }
+    out[i] = usqrt_trunc(d);
+}
+
+cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st) {
+    if (B == 0 || T == 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DtwSmem));
+    if (e != cudaSuccess) return e;
+    const u32 tiles = (T + kTileT - 1) / kTileT;
+    u32 gy = ((u32)num_sms * 2 + tiles - 1) / tiles;
+    const u32 ugroups = (B + kDtwWarps - 1) / kDtwWarps;
+    if (gy > ugroups) gy = ugroups;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid(tiles, gy);
+    dtw_kernel<<<grid, kDtwWarps * 32, sizeof(DtwSmem), st>>>(static_cast<const unsigned char *>(in_ftr), B,
+                                                             static_cast<const unsigned char *>(bank), T, slot_stride,
+                                                             flags, score, best, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    best_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(best, B);
+    return cudaGetLastError();
+}
+cudaError_t launch_best_final(const u64 *best, u32 B, u32 *best_idx, u32 *best_dis, u32 *cmd, const u8 *status,
+                              cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    best_final_kernel<<<(B + 255) / 256, 256, 0, st>>>(best, B, best_idx, best_dis, cmd, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_status(const u32 *seg_off, const void *ftr, u32 B, u8 *status, cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    status_kernel<<<(B + 255) / 256, 256, 0, st>>>(seg_off, static_cast<const unsigned char *>(ftr), B, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_get_dis(const s16 *a, const s16 *b, u32 n, u32 *out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    get_dis_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace srk
+
+// ---- K3 placeholder: banded DP launcher (implemented in sr_dtw_band.cu once parity-checked) --------
+namespace srk {
+__attribute__((weak)) cudaError_t launch_dtw_band(const void *, u32, const void *, u32, u32, u32, int, u32 *, u64 *, int,
+                                                  cudaStream_t) {
+    return cudaErrorNotSupported;
+}
+}  // namespace srk

@@ -1,0 +1,407 @@
+// sr_mfcc.cu -- K1: batched get_mfcc (Src/Speech_Recog/MFCC.C:86-191) with the bit-exact
+// fixed-point radix-4 FFT of Src/BSP/cr4_fft_1024_stm32.s:95-281 done in registers/shared memory.
+//
+// Work decomposition (B200: 148 SMs, one persistent CTA per SM):
+//   * a CTA walks utterances b = blockIdx.x, +gridDim.x, ...; a PRODUCER warp stages each
+//     utterance's PCM segment [start-1, end) into a 3-deep shared-memory ring with 1-D bulk
+//     async copies (TMA engine, cp.async.bulk + mbarrier complete_tx), so every PCM sample is
+//     read from HBM exactly once although frames overlap by 50 %;
+//   * 16 CONSUMER warps take frames round-robin from the CTA's concatenated frame stream,
+//     one frame per warp: pre-emphasis + Hamming (MFCC.C:115-124), FFT, |.| (MFCC.C:49-60),
+//     energy (MFCC.C:128-133), 24 triangular filters (MFCC.C:136-162), log (MFCC.C:165-170),
+//     DCT (MFCC.C:173-183) -> 12 x s16.
+//
+// FFT blocking (validated against the asm restatement by tools/fft_block_model.py):
+//   stage 0 collapses for a real frame of <= 256 samples: y0[4*idx+m] = (w[bitrev8(idx)]>>2, 0);
+//   block A (G,q1): 4 stage-1 butterflies (groups 4G+m2) + 4 stage-2 butterflies (q2=q1+4*m1)
+//                   on 16 register-resident points, 64 blocks/frame = 2 per lane;
+//   exchange through a padded shared buffer (conflict-free both ways);
+//   block B (q3):   4 stage-3 butterflies (groups m4) + 4 stage-4 butterflies (q4=q3+64*m3),
+//                   only output legs 0,1 (bins < 512, MFCC.C:49) are formed.
+#include "sr_common.cuh"
+
+namespace srk {
+
+constexpr int kConsumerWarps = 16;
+constexpr int kMfccThreads = (kConsumerWarps + 1) * 32;
+constexpr int kNBuf = 3;
+constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
+constexpr int kFftWords = 1024 + 64;         // +4 words per 64
+constexpr int kEWords = 512 + 64;            // +4 words per 32
+
+struct __align__(16) MfccSmem {
+    unsigned char pcm[kNBuf][kPcmBufBytes];
+    int2 tw[340 * 3];
+    u32 log_thr[2220];
+    u16 tri_even[512];
+    u16 tri_odd[512];
+    u32 fftbuf[kConsumerWarps][kFftWords];
+    u32 ebuf[kConsumerWarps][kEWords];
+    s32 wq[kConsumerWarps][160];
+    u32 seq[kConsumerWarps][2][64];
+    u32 lg[kConsumerWarps][32];
+    u64 full[kNBuf];
+    u64 empty[kNBuf];
+    s32 meta[kNBuf][4];                      // {F, sample index of x[start-1] in the buffer, mid, -}
+};
+
+__device__ __forceinline__ int padF(int e) { return e + ((e >> 6) << 2); }
+__device__ __forceinline__ int padE(int k) { return k + ((k >> 5) << 2); }
+
+// (u32)(log((double)v)*100) via the exact threshold table (MFCC.C:168; log(0) pinned to 0)
+__device__ __forceinline__ u32 log100(u32 v, const u32 *thr) {
+    if (v == 0) return 0;
+    int L = (int)(__log2f(__uint2float_rn(v)) * 69.31471805599453f);
+    L = max(0, min(L, 2218));
+    while (v < thr[L]) --L;                       // thr[0] = 1 <= v, so this stops at L >= 0
+    while (L < 2218 && v >= thr[L + 1]) ++L;
+    return (u32)L;
+}
+
+// frame count of a segment, MFCC.C:102-107 (u32 wrap, u16 truncation); 0 = rejected / empty
+__device__ __forceinline__ int mfcc_frames(u32 start, u32 end, u32 U) {
+    if (start == SR_SEG_NULL || end == SR_SEG_NULL || end > U || start > end) return 0;
+    u32 len = end - start;
+    if (len < SR_FRAME_LEN) return 0;             // loop MFCC.C:113 never runs
+    u32 n = (len - SR_FRAME_LEN) / SR_FRAME_MOV + 1u;
+    return n > SR_VV_FRM_MAX ? 0 : (int)n;
+}
+
+__global__ void __launch_bounds__(kMfccThreads, 1)
+mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg, u32 seg_stride,
+            const atap_tag *__restrict__ atap, unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MfccSmem &sm = *reinterpret_cast<MfccSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time: tables to shared memory, barriers ------------------------------------------
+    for (int i = threadIdx.x; i < 340 * 3; i += blockDim.x) sm.tw[i] = tab->tw[i];
+    for (int i = threadIdx.x; i < 2220; i += blockDim.x) sm.log_thr[i] = tab->log_thr[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { sm.tri_even[i] = tab->tri_even[i]; sm.tri_odd[i] = tab->tri_odd[i]; }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kNBuf; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const size_t total_bytes = (size_t)B * U * 2;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+
+    // ================================ producer warp =============================================
+    if (warp == kConsumerWarps) {
+        int it = 0;
+        for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+            const int s = it % kNBuf;
+            if (it >= kNBuf) mbar_wait(&sm.empty[s], ((it / kNBuf) - 1) & 1);
+            const u32 st = seg[(size_t)b * seg_stride], en = seg[(size_t)b * seg_stride + 1];
+            const int F = mfcc_frames(st, en, U);
+            const u32 mid = atap[b].mid_val;
+            if (lane == 0) *reinterpret_cast<u16 *>(ftr + (size_t)b * kFtrBytes + 2) = (u16)F;   // MFCC.C:106,189
+            if (F == 0) {
+                if (lane == 0) { sm.meta[s][0] = 0; sm.meta[s][1] = 0; sm.meta[s][2] = (s32)mid; mbar_arrive(&sm.full[s]); }
+                continue;
+            }
+            // bytes [lo,hi) of the batch: samples start-1 .. start+80(F-1)+159 of utterance b
+            long long first = (long long)b * U + st - 1;           // may be -1 for b=0,start=0
+            const long long last = (long long)b * U + st + 80ll * (F - 1) + 160;   // exclusive
+            unsigned char *dst = sm.pcm[s];
+            int off = 0;
+            if (first < 0) {                                       // x[-1] of the whole batch: reference reads
+                if (lane == 0) reinterpret_cast<u16 *>(dst)[7] = (u16)mid;   // out of bounds (MFCC.C:119); pinned to mid
+                first = 0; off = 8;                                // sample 0 lands at dst+16 (index 8), x[-1] at index 7
+                dst += 16;
+            }
+            const size_t lo = (size_t)first * 2, hi = (size_t)last * 2;
+            if (base_aligned) {
+                const size_t lo_al = lo & ~(size_t)15;
+                size_t hi_al = (hi + 15) & ~(size_t)15;
+                const size_t lim = total_bytes & ~(size_t)15;
+                if (hi_al > lim) hi_al = lim;
+                const u32 nbytes = (u32)(hi_al - lo_al);
+                const int shift = (int)((lo - lo_al) >> 1);
+                if (lane == 0) {
+                    sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid;
+                    sm.meta[s][1] = (off ? 7 : shift);             // index of x[start-1] (7 = slot just below dst+16)
+                }
+                // tail beyond the last whole 16-byte granule of the allocation: plain loads
+                if (hi > hi_al) {
+                    const u16 *g = reinterpret_cast<const u16 *>(reinterpret_cast<const unsigned char *>(pcm) + hi_al);
+                    u16 *d = reinterpret_cast<u16 *>(dst + (hi_al - lo_al));
+                    const int n = (int)((hi - hi_al) >> 1);
+                    if (lane < n) d[lane] = g[lane];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&sm.full[s], nbytes);
+                    bulk_g2s(dst, reinterpret_cast<const unsigned char *>(pcm) + lo_al, nbytes, &sm.full[s]);
+                }
+            } else {                                               // unaligned batch base: cooperative plain copy
+                const u16 *g = pcm + first;
+                u16 *d = reinterpret_cast<u16 *>(dst);
+                const int n = (int)(last - first);
+                for (int i = lane; i < n; i += 32) d[i] = g[i];
+                __syncwarp();
+                if (lane == 0) {
+                    sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid; sm.meta[s][1] = off ? 7 : 0;
+                    mbar_arrive(&sm.full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================ consumer warps ============================================
+    u32 *fb = sm.fftbuf[warp];
+    u32 *eb = sm.ebuf[warp];
+    s32 *wq = sm.wq[warp];
+    const int q1 = lane & 3;
+    // stage-1 twiddles (table block N=16, triple q1: legs K2 -> p2, K1 -> p1; leg 3 is all-zero)
+    const int2 k1_2 = sm.tw[q1 * 3 + 1], k1_1 = sm.tw[q1 * 3 + 2];
+    const u32 hm0 = tab->hamm[lane], hm1 = tab->hamm[lane + 32], hm2 = tab->hamm[lane + 64],
+              hm3 = tab->hamm[lane + 96], hm4 = tab->hamm[lane + 128];
+    const int sp_e = tab->split_even[lane], sp_o = tab->split_odd[lane];
+    int flo = 0, fhi = -1, fpar = 0;
+    if (lane < 24) { flo = tab->seq_lo[lane]; fhi = tab->seq_hi[lane]; fpar = lane & 1; }
+    // DCT role: lanes 0..23 -> coefficient c = lane>>1, half = lane&1 (12 filters each)
+    s32 dctk[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) dctk[i] = (lane < 24) ? (s32)tab->dct[(lane >> 1) * 24 + (lane & 1) * 12 + i] : 0;
+
+    u32 gidx = 0;   // frames of this CTA's stream before the current utterance
+    int it = 0;
+    for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+        const int s = it % kNBuf;
+        mbar_wait(&sm.full[s], (it / kNBuf) & 1);
+        const int F = sm.meta[s][0];
+        const int off = sm.meta[s][1];
+        const s32 mid = sm.meta[s][2];
+        const u16 *x = reinterpret_cast<const u16 *>(sm.pcm[s]) + off;   // x[0] = sample start-1
+        unsigned char *out_rows = ftr + (size_t)b * kFtrBytes + 4;
+
+        for (int f = (int)((warp - (int)(gidx % kConsumerWarps) + kConsumerWarps) % kConsumerWarps); f < F;
+             f += kConsumerWarps) {
+            const u16 *xf = x + 80 * f;                                  // xf[i] = vc_dat[i-1]
+            // ---- pre-emphasis + Hamming, MFCC.C:115-124; keep w>>2 (stage-0 output) ------------
+            {
+                const u32 hm[5] = {hm0, hm1, hm2, hm3, hm4};
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int i = lane + 32 * k;
+                    const s32 cur = (s32)((u32)xf[i + 1] - (u32)mid), prv = (s32)((u32)xf[i] - (u32)mid);
+                    const s32 t = (s32)((u32)cur - (u32)((s32)((u32)prv * 95u) / 100));
+                    const s32 w = (s32)(s16)((s32)((u32)t * hm[k]) / 1000);
+                    wq[i] = w >> 2;                                       // BUTFLY4ZERO_OPT with B=C=D=0
+                }
+            }
+            __syncwarp();
+
+            // ---- block A: stages 1+2 -----------------------------------------------------------
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int G = (lane >> 2) + 8 * pass;
+                const int r0 = (int)(__brev((u32)G) >> 28);
+                u32 vr[4][4], vi[4][4];                                    // [m2][m1]
+#pragma unroll
+                for (int m2 = 0; m2 < 4; ++m2) {
+                    const int r = r0 + 16 * (((m2 & 1) << 1) | (m2 >> 1));
+                    const u32 a = (u32)wq[r];
+                    const u32 c = (u32)wq[r + 64];
+                    u32 Cr, Ci, Br = 0, Bi = 0;
+                    cxmul(Cr, Ci, c, 0u, (u32)k1_2.x, (u32)k1_2.y);
+                    if ((m2 & 1) == 0) {                                   // r+128 < 160 only for r < 32
+                        const u32 bb = (u32)wq[r + 128];
+                        cxmul(Br, Bi, bb, 0u, (u32)k1_1.x, (u32)k1_1.y);
+                    }
+                    u32 o[8];
+                    cxadda4<14>(a, 0u, Br, Bi, Cr, Ci, 0u, 0u, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+#pragma unroll
+                    for (int m1 = 0; m1 < 4; ++m1) { vr[m2][m1] = sx16(o[2 * m1]); vi[m2][m1] = sx16(o[2 * m1 + 1]); }
+                }
+#pragma unroll
+                for (int m1 = 0; m1 < 4; ++m1) {
+                    const int q2 = q1 + 4 * m1;
+                    const int2 *k = &sm.tw[(4 + q2) * 3];
+                    const int2 k3 = k[0], k2 = k[1], k1 = k[2];
+                    u32 Dr, Di, Cr, Ci, Br, Bi;
+                    cxmul(Dr, Di, vr[3][m1], vi[3][m1], (u32)k3.x, (u32)k3.y);
+                    cxmul(Cr, Ci, vr[2][m1], vi[2][m1], (u32)k2.x, (u32)k2.y);
+                    cxmul(Br, Bi, vr[1][m1], vi[1][m1], (u32)k1.x, (u32)k1.y);
+                    u32 o[8];
+                    cxadda4<14>(vr[0][m1], vi[0][m1], Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                    const int e0 = 64 * G + q2;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) fb[padF(e0 + 16 * m)] = pack16(o[2 * m], o[2 * m + 1]);
+                }
+            }
+            __syncwarp();
+
+            // ---- block B: stages 3+4, magnitude, energy ---------------------------------------
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int q3 = lane + 32 * pass;
+                u32 vr[4][4], vi[4][4];                                    // [m4][m3]
+                const int2 *k = &sm.tw[(20 + q3) * 3];
+                const int2 k3 = k[0], k2 = k[1], k1 = k[2];
+#pragma unroll
+                for (int m4 = 0; m4 < 4; ++m4) {
+                    u32 p[4];
+#pragma unroll
+                    for (int m3 = 0; m3 < 4; ++m3) p[m3] = fb[padF(256 * m4 + q3 + 64 * m3)];
+                    u32 Dr, Di, Cr, Ci, Br, Bi;
+                    cxmul(Dr, Di, lo16s(p[3]), hi16s(p[3]), (u32)k3.x, (u32)k3.y);
+                    cxmul(Cr, Ci, lo16s(p[2]), hi16s(p[2]), (u32)k2.x, (u32)k2.y);
+                    cxmul(Br, Bi, lo16s(p[1]), hi16s(p[1]), (u32)k1.x, (u32)k1.y);
+                    u32 o[8];
+                    cxadda4<14>(lo16s(p[0]), hi16s(p[0]), Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+#pragma unroll
+                    for (int m3 = 0; m3 < 4; ++m3) { vr[m4][m3] = sx16(o[2 * m3]); vi[m4][m3] = sx16(o[2 * m3 + 1]); }
+                }
+#pragma unroll
+                for (int m3 = 0; m3 < 4; ++m3) {
+                    const int q4 = q3 + 64 * m3;
+                    const int2 *kk = &sm.tw[(84 + q4) * 3];
+                    const int2 j3 = kk[0], j2 = kk[1], j1 = kk[2];
+                    u32 Dr, Di, Cr, Ci, Br, Bi;
+                    cxmul(Dr, Di, vr[3][m3], vi[3][m3], (u32)j3.x, (u32)j3.y);
+                    cxmul(Cr, Ci, vr[2][m3], vi[2][m3], (u32)j2.x, (u32)j2.y);
+                    cxmul(Br, Bi, vr[1][m3], vi[1][m3], (u32)j1.x, (u32)j1.y);
+                    u32 o[8];
+                    cxadda4<14>(vr[0][m3], vi[0][m3], Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                    // bins q4 (leg 0) and q4+256 (leg 1); legs 2,3 are bins >= 512, unused (MFCC.C:49)
+                    const u32 m0 = mag10(sx16(o[0]), sx16(o[1]));
+                    const u32 m1 = mag10(sx16(o[2]), sx16(o[3]));
+                    eb[padE(q4)] = m0 * m0;                                 // MFCC.C:131 (u32 wrap)
+                    eb[padE(q4 + 256)] = m1 * m1;
+                }
+            }
+            __syncwarp();
+
+            // ---- triangular filters, MFCC.C:136-162: lane owns bins [16*lane, 16*lane+16) ------
+            {
+                u32 E[16];
+                const uint4 *e4 = reinterpret_cast<const uint4 *>(eb + 16 * lane + 4 * (lane >> 1));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const uint4 v = e4[j]; E[4 * j] = v.x; E[4 * j + 1] = v.y; E[4 * j + 2] = v.z; E[4 * j + 3] = v.w; }
+                const uint4 *te4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
+                const uint4 *to4 = reinterpret_cast<const uint4 *>(sm.tri_odd + 16 * lane);
+                u32 te[8], to[8];
+                { const uint4 a = te4[0], c = te4[1]; te[0] = a.x; te[1] = a.y; te[2] = a.z; te[3] = a.w; te[4] = c.x; te[5] = c.y; te[6] = c.z; te[7] = c.w; }
+                { const uint4 a = to4[0], c = to4[1]; to[0] = a.x; to[1] = a.y; to[2] = a.z; to[3] = a.w; to[4] = c.x; to[5] = c.y; to[6] = c.z; to[7] = c.w; }
+                u32 s0e = 0, s1e = 0, s0o = 0, s1o = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const u32 we = (i & 1) ? (te[i >> 1] >> 16) : (te[i >> 1] & 0xFFFFu);
+                    const u32 wo = (i & 1) ? (to[i >> 1] >> 16) : (to[i >> 1] & 0xFFFFu);
+                    const u32 ve = (E[i] * we) / 100u, vo = (E[i] * wo) / 100u;
+                    if (i < sp_e) s0e += ve; else s1e += ve;
+                    if (i < sp_o) s0o += vo; else s1o += vo;
+                }
+                *reinterpret_cast<uint2 *>(&sm.seq[warp][0][2 * lane]) = make_uint2(s0e, s1e);
+                *reinterpret_cast<uint2 *>(&sm.seq[warp][1][2 * lane]) = make_uint2(s0o, s1o);
+            }
+            __syncwarp();
+            // ---- filter totals + log, MFCC.C:165-170 -------------------------------------------
+            {
+                u32 acc = 0;
+                for (int e = flo; e <= fhi; ++e) acc += sm.seq[warp][fpar][e];
+                sm.lg[warp][lane] = (lane < 24) ? log100(acc, sm.log_thr) : 0u;
+            }
+            __syncwarp();
+            // ---- DCT, MFCC.C:173-183: each term truncated toward zero, s16 accumulate ----------
+            {
+                const u32 *lgp = &sm.lg[warp][(lane & 1) * 12];
+                s32 acc = 0;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) acc += ((s32)lgp[i] * dctk[i]) / 100;
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+                if (lane < 24 && (lane & 1) == 0)
+                    *reinterpret_cast<s16 *>(out_rows + (size_t)f * kRowBytes + (lane >> 1) * 2) = (s16)acc;
+            }
+            __syncwarp();
+        }
+        gidx += (u32)F;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
+}
+
+// ---- generic (unpruned) FFT + magnitude: the reference's global `fft` (MFCC.C:27-62) -----------
+// One warp per frame, all five passes in shared memory exactly as the asm orders them. Not on the
+// hot path; it exists for the secondary drop-in symbol and as an on-device cross-check of the
+// pruned blocking above with arbitrary (complex, full-length) inputs.
+__global__ void __launch_bounds__(128)
+fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, const s16 *__restrict__ frames, u32 len,
+                   u32 n, u32 *__restrict__ raw_out /*[n][1024] or NULL*/, u32 *__restrict__ mag /*[n][512] or NULL*/,
+                   const DevTables *__restrict__ tab) {
+    __shared__ u32 buf[4][1024];
+    __shared__ u32 src[4][1024];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 fr = blockIdx.x * 4 + warp;
+    if (fr >= n) return;
+    u32 *x = src[warp], *y = buf[warp];
+    for (int i = lane; i < 1024; i += 32) {
+        u32 v;
+        if (in) v = in[(size_t)fr * 1024 + i];
+        else v = (u32)i < len ? (u32)(u16)frames[(size_t)fr * len + i] : 0u;     // MFCC.C:37-45
+        x[i] = v;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 256; idx += 32) {                                 // .s:226-232
+        const int j = (int)(__brev((u32)idx) >> 24);
+        const u32 A = x[j], C = x[j + 256], Bv = x[j + 512], D = x[j + 768];
+        u32 o[8];
+        cxadda4<0>(lo16s(A), hi16s(A), lo16s(Bv), hi16s(Bv), lo16s(C), hi16s(C), lo16s(D), hi16s(D),
+                   o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) y[4 * idx + m] = pack16(o[2 * m], o[2 * m + 1]);
+    }
+    __syncwarp();
+    int toff = 0;
+    for (int s = 4; s <= 256; s <<= 2) {                                         // .s:254-279
+        for (int t = lane; t < 256; t += 32) {
+            const int q = t % s, base = (t / s) * 4 * s;
+            const int2 k3 = tab->tw[(toff + q) * 3], k2 = tab->tw[(toff + q) * 3 + 1], k1 = tab->tw[(toff + q) * 3 + 2];
+            const u32 p0 = y[base + q], p1 = y[base + q + s], p2 = y[base + q + 2 * s], p3 = y[base + q + 3 * s];
+            u32 Dr, Di, Cr, Ci, Br, Bi, o[8];
+            cxmul(Dr, Di, lo16s(p3), hi16s(p3), (u32)k3.x, (u32)k3.y);
+            cxmul(Cr, Ci, lo16s(p2), hi16s(p2), (u32)k2.x, (u32)k2.y);
+            cxmul(Br, Bi, lo16s(p1), hi16s(p1), (u32)k1.x, (u32)k1.y);
+            cxadda4<14>(lo16s(p0), hi16s(p0), Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) y[base + q + m * s] = pack16(o[2 * m], o[2 * m + 1]);
+        }
+        __syncwarp();
+        toff += s;
+    }
+    if (raw_out) for (int i = lane; i < 1024; i += 32) raw_out[(size_t)fr * 1024 + i] = y[i];
+    if (mag) for (int i = lane; i < 512; i += 32) mag[(size_t)fr * 512 + i] = mag10(lo16s(y[i]), hi16s(y[i]));
+}
+
+// ---- host launchers -----------------------------------------------------------------------------
+cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
+                        void *ftr, int num_sms, cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfccSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const DevTables *tab = dev_tables();
+    if (!tab) return cudaErrorInitializationError;
+    const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
+    mfcc_kernel<<<grid, kMfccThreads, sizeof(MfccSmem), st>>>(pcm, U, B, seg, seg_stride, atap,
+                                                              static_cast<unsigned char *>(ftr), tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
+                               cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const DevTables *tab = dev_tables();
+    if (!tab) return cudaErrorInitializationError;
+    fft_generic_kernel<<<(n + 3) / 4, 128, 0, st>>>(in_packed, frames, len, n, raw_out, mag, tab);
+    return cudaGetLastError();
+}
+
+}  // namespace srk

@@ -1,0 +1,72 @@
+// sr_tables.cu -- builds the constant tables of the MFCC path once per device and keeps them in
+// global memory (kernels stage what they need into shared memory). Everything derives from the
+// closed-form tables of tools/gen_tables.py (sr_tables.h); see there for the reference citations.
+#include <mutex>
+#include <string.h>
+#include "sr_common.cuh"
+#include "sr_tables.h"
+
+namespace srk {
+
+static void build_tables(DevTables &t) {
+    memset(&t, 0, sizeof t);
+    for (int i = 0; i < 340 * 3; ++i) {
+        const int ka = sr_tab_twiddle[2 * i], kb = sr_tab_twiddle[2 * i + 1];
+        t.tw[i] = make_int2(ka + kb, kb);
+    }
+    for (int i = 0; i < 2220; ++i) t.log_thr[i] = sr_tab_log_thr[i];
+    for (int i = 0; i < 160; ++i) t.hamm[i] = sr_tab_hamm[i];
+    for (int i = 0; i < 512; ++i) { t.tri_even[i] = sr_tab_tri_even[i]; t.tri_odd[i] = sr_tab_tri_odd[i]; }
+    for (int i = 0; i < 288; ++i) t.dct[i] = sr_tab_dct[i];
+    // Filter ranges, MFCC.C:136-162. Even filters h=0,2,..,22 tile [0,cen[1]) [cen[1],cen[3]) .. [cen[21],cen[23])
+    // and use tri_even; odd filters h=1,3,..,23 tile [cen[0],cen[2]) .. [cen[20],cen[22]) [cen[22],512), tri_odd.
+    const uint16_t *cen = sr_tab_tri_cen;
+    int bnd[2][13];
+    bnd[0][0] = 0;
+    for (int j = 1; j <= 12; ++j) bnd[0][j] = cen[2 * j - 1];
+    for (int j = 0; j < 12; ++j) bnd[1][j] = cen[2 * j];
+    bnd[1][12] = 512;
+    for (int par = 0; par < 2; ++par) {
+        u8 *split = par ? t.split_odd : t.split_even;
+        for (int L = 0; L < 32; ++L) {
+            split[L] = 16;                                   // no boundary: everything in partial sum 0
+            for (int j = 0; j <= 12; ++j)
+                if (bnd[par][j] >= 16 * L && bnd[par][j] <= 16 * L + 16) split[L] = (u8)(bnd[par][j] - 16 * L);
+        }
+        for (int j = 0; j < 12; ++j) {
+            const int h = 2 * j + par, lo = bnd[par][j], hi = bnd[par][j + 1];
+            const int Ll = lo >> 4, Lh = (hi - 1) >> 4;
+            t.seq_lo[h] = (u8)(2 * Ll + ((lo - 16 * Ll) >= split[Ll] ? 1 : 0));
+            t.seq_hi[h] = (u8)(2 * Lh + ((hi - 1 - 16 * Lh) >= split[Lh] ? 1 : 0));
+        }
+    }
+}
+
+const DevTables *dev_tables() {
+    static std::mutex mu;
+    static DevTables *ptr[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!ptr[dev]) {
+        DevTables *h = new DevTables;
+        build_tables(*h);
+        DevTables *d = nullptr;
+        if (cudaMalloc(&d, sizeof(DevTables)) != cudaSuccess) { delete h; return nullptr; }
+        if (cudaMemcpy(d, h, sizeof(DevTables), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); delete h; return nullptr; }
+        delete h;
+        ptr[dev] = d;
+    }
+    return ptr[dev];
+}
+
+// host-side copy for unit tests of the filter partition (no GPU needed)
+extern "C" void sr_debug_filter_partition(uint8_t *split_even, uint8_t *split_odd, uint8_t *seq_lo, uint8_t *seq_hi) {
+    DevTables *h = new DevTables;
+    build_tables(*h);
+    memcpy(split_even, h->split_even, 32); memcpy(split_odd, h->split_odd, 32);
+    memcpy(seq_lo, h->seq_lo, 24); memcpy(seq_hi, h->seq_hi, 24);
+    delete h;
+}
+
+}  // namespace srk

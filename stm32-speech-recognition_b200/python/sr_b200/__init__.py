@@ -1,0 +1,273 @@
+"""ctypes binding of libspeech_b200.so (include/speech_recog.h, include/sr_synth.h).
+
+Plumbing for tests/ and bench.py only -- the product is the C-ABI library itself. Nothing here
+computes: every call forwards to the CUDA kernels and raises if the library or a GPU is missing
+(there is no CPU fallback). Struct layouts mirror the reference's VAD.H:10-22 / MFCC.H:18-25.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.normpath(os.path.join(_HERE, "..", ".."))
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libspeech_b200.so")
+
+FRAME_LEN, FRAME_MOV, MFCC_NUM, VV_FRM_MAX = 160, 80, 12, 119
+FTR_BYTES = 2860
+SEG_NULL = 0xFFFFFFFF
+DIS_ERR = 0xFFFFFFFF
+SAVE_MASK = 12345
+DTW_CHECK_SIGN, DTW_BAND = 1, 2
+
+ATAP_DTYPE = np.dtype([("mid_val", "<u4"), ("n_thl", "<u2"), ("z_thl", "<u2"), ("s_thl", "<u4")])
+FTR_DTYPE = np.dtype([("save_sign", "<u2"), ("frm_num", "<u2"), ("mfcc_dat", "<i2", (VV_FRM_MAX * MFCC_NUM,))])
+assert ATAP_DTYPE.itemsize == 12 and FTR_DTYPE.itemsize == FTR_BYTES
+
+
+class RecogOut(C.Structure):
+    _fields_ = [("atap", C.c_void_p), ("seg_off", C.c_void_p), ("ftr", C.c_void_p), ("score", C.c_void_p),
+                ("best_idx", C.c_void_p), ("best_dis", C.c_void_p), ("cmd", C.c_void_p), ("status", C.c_void_p)]
+
+
+class ValidTag(C.Structure):
+    _fields_ = [("start", C.c_void_p), ("end", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built: run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libspeech_b200.so is not built (%s); run __graft_entry__.build()" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.sr_create.argtypes = [i32, C.POINTER(vp)]
+        L.sr_destroy.argtypes = [vp]
+        L.sr_set_stream.argtypes = [vp, vp]
+        L.sr_sync.argtypes = [vp]
+        L.sr_last_error.argtypes = [vp]
+        L.sr_last_error.restype = C.c_char_p
+        L.sr_host_alloc.argtypes = [C.c_size_t]
+        L.sr_host_alloc.restype = vp
+        L.sr_host_free.argtypes = [vp]
+        L.sr_launch_count.argtypes = [vp]
+        L.sr_launch_count.restype = u64
+        L.sr_set_bank.argtypes = [vp, vp, u32, u32]
+        L.sr_set_bank_dev.argtypes = [vp, vp, u32, u32]
+        for name in ("sr_noise_atap_batch", "sr_noise_atap_batch_dev"):
+            getattr(L, name).argtypes = [vp, vp, u32, u32, u32, vp]
+        for name in ("sr_vad_batch", "sr_vad_batch_dev"):
+            getattr(L, name).argtypes = [vp, vp, u32, u32, u32, vp, vp]
+        for name in ("sr_mfcc_batch", "sr_mfcc_batch_dev"):
+            getattr(L, name).argtypes = [vp, vp, u32, u32, vp, u32, vp, vp]
+        for name in ("sr_dtw_batch", "sr_dtw_batch_dev"):
+            getattr(L, name).argtypes = [vp, vp, u32, u32, i32, vp, vp, vp]
+        for name in ("sr_recognise_batch", "sr_recognise_batch_dev"):
+            getattr(L, name).argtypes = [vp, vp, u32, u32, u32, C.POINTER(RecogOut)]
+        L.sr_fft_mag_batch.argtypes = [vp, vp, u32, u32, vp]
+        L.sr_fft_raw_batch.argtypes = [vp, vp, u32, vp]
+        L.sr_get_dis_batch.argtypes = [vp, vp, vp, u32, vp]
+        L.sr_synth_pcm_host.argtypes = [vp, u32, u32, u64, u32]
+        L.sr_synth_pcm_dev.argtypes = [vp, u32, u32, u64, u32, vp]
+        L.sr_synth_ftr_host.argtypes = [vp, u32, u32, u64, u32, u32]
+        L.noise_atap.argtypes = [vp, C.c_uint16, vp]
+        L.noise_atap.restype = None
+        L.VAD.argtypes = [vp, C.c_uint16, vp, vp]
+        L.VAD.restype = None
+        L.get_mfcc.argtypes = [vp, vp, vp]
+        L.get_mfcc.restype = None
+        L.dtw.argtypes = [vp, vp]
+        L.dtw.restype = u32
+        L.fft.argtypes = [vp, C.c_uint16]
+        L.fft.restype = C.POINTER(C.c_uint32)
+        L.get_dis.argtypes = [vp, vp]
+        L.get_dis.restype = u32
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    """void* of a numpy array (must be C-contiguous) or an int device pointer / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+class SrError(RuntimeError):
+    pass
+
+
+class Handle:
+    """RAII wrapper of sr_handle. `device` is the CUDA ordinal."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().sr_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise SrError("sr_create failed (%d): %s" % (rc, lib().sr_last_error(None).decode()))
+        self.n_slot = 0
+
+    def close(self):
+        if self._h:
+            lib().sr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SrError("libspeech_b200 call failed (%d): %s" % (rc, lib().sr_last_error(self._h).decode()))
+
+    # -- plumbing
+    def set_stream(self, stream_ptr):
+        self._ck(lib().sr_set_stream(self._h, _p(stream_ptr)))
+
+    def sync(self):
+        self._ck(lib().sr_sync(self._h))
+
+    def launch_count(self):
+        return int(lib().sr_launch_count(self._h))
+
+    def set_bank(self, bank, n_slot, slot_stride):
+        self._ck(lib().sr_set_bank(self._h, _p(bank), n_slot, slot_stride))
+        self.n_slot = n_slot
+
+    def set_bank_dev(self, bank_ptr, n_slot, slot_stride):
+        self._ck(lib().sr_set_bank_dev(self._h, _p(bank_ptr), n_slot, slot_stride))
+        self.n_slot = n_slot
+
+    # -- host-buffer batched entry points (numpy in / numpy out)
+    def noise_atap(self, pcm, n_len, atap=None):
+        B, U = pcm.shape
+        if atap is None:
+            atap = np.zeros(B, ATAP_DTYPE)
+        self._ck(lib().sr_noise_atap_batch(self._h, _p(pcm), U, B, n_len, _p(atap)))
+        return atap
+
+    def vad(self, pcm, atap, buf_len=None):
+        B, U = pcm.shape
+        seg = np.zeros((B, 3, 2), np.uint32)
+        self._ck(lib().sr_vad_batch(self._h, _p(pcm), U, B, U if buf_len is None else buf_len, _p(atap), _p(seg)))
+        return seg
+
+    def mfcc(self, pcm, seg, atap, ftr=None):
+        B, U = pcm.shape
+        seg = np.ascontiguousarray(seg, np.uint32).reshape(B, -1)
+        if ftr is None:
+            ftr = np.zeros(B, FTR_DTYPE)
+        self._ck(lib().sr_mfcc_batch(self._h, _p(pcm), U, B, _p(seg), seg.shape[1], _p(atap), _p(ftr)))
+        return ftr
+
+    def dtw(self, ftr_in, flags=0, band_r=0, want_score=True, want_best=True):
+        B = ftr_in.shape[0]
+        score = np.zeros((B, self.n_slot), np.uint32) if want_score else None
+        bi = np.zeros(B, np.uint32) if want_best else None
+        bd = np.zeros(B, np.uint32) if want_best else None
+        self._ck(lib().sr_dtw_batch(self._h, _p(ftr_in), B, flags, band_r, _p(score), _p(bi), _p(bd)))
+        return score, bi, bd
+
+    def recognise(self, pcm, n_len=2400, want=("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")):
+        B, U = pcm.shape
+        out = {}
+        if "atap" in want:
+            out["atap"] = np.zeros(B, ATAP_DTYPE)
+        if "seg_off" in want:
+            out["seg_off"] = np.zeros((B, 3, 2), np.uint32)
+        if "ftr" in want:
+            out["ftr"] = np.zeros(B, FTR_DTYPE)
+        if "score" in want:
+            out["score"] = np.zeros((B, self.n_slot), np.uint32)
+        for k in ("best_idx", "best_dis", "cmd"):
+            if k in want:
+                out[k] = np.zeros(B, np.uint32)
+        if "status" in want:
+            out["status"] = np.zeros(B, np.uint8)
+        ro = RecogOut(*[(_p(out[k]) if k in out else None) for k in
+                        ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
+        self._ck(lib().sr_recognise_batch(self._h, _p(pcm), U, B, n_len, C.byref(ro)))
+        return out
+
+    def fft_mag(self, frames):
+        n, length = frames.shape
+        mag = np.zeros((n, 512), np.uint32)
+        self._ck(lib().sr_fft_mag_batch(self._h, _p(frames), length, n, _p(mag)))
+        return mag
+
+    def fft_raw(self, packed):
+        n = packed.shape[0]
+        out = np.zeros((n, 1024), np.uint32)
+        self._ck(lib().sr_fft_raw_batch(self._h, _p(packed), n, _p(out)))
+        return out
+
+    def get_dis(self, a, b):
+        n = a.shape[0]
+        out = np.zeros(n, np.uint32)
+        self._ck(lib().sr_get_dis_batch(self._h, _p(a), _p(b), n, _p(out)))
+        return out
+
+    # -- device-pointer entry points (ints / torch data_ptr()), asynchronous on the handle's stream
+    def noise_atap_dev(self, pcm_ptr, U, B, n_len, atap_ptr):
+        self._ck(lib().sr_noise_atap_batch_dev(self._h, _p(pcm_ptr), U, B, n_len, _p(atap_ptr)))
+
+    def vad_dev(self, pcm_ptr, U, B, buf_len, atap_ptr, seg_ptr):
+        self._ck(lib().sr_vad_batch_dev(self._h, _p(pcm_ptr), U, B, buf_len, _p(atap_ptr), _p(seg_ptr)))
+
+    def mfcc_dev(self, pcm_ptr, U, B, seg_ptr, seg_stride, atap_ptr, ftr_ptr):
+        self._ck(lib().sr_mfcc_batch_dev(self._h, _p(pcm_ptr), U, B, _p(seg_ptr), seg_stride, _p(atap_ptr), _p(ftr_ptr)))
+
+    def dtw_dev(self, ftr_ptr, B, flags, band_r, score_ptr, bi_ptr, bd_ptr):
+        self._ck(lib().sr_dtw_batch_dev(self._h, _p(ftr_ptr), B, flags, band_r, _p(score_ptr), _p(bi_ptr), _p(bd_ptr)))
+
+    def recognise_dev(self, pcm_ptr, U, B, n_len, **ptrs):
+        ro = RecogOut(*[_p(ptrs.get(k)) for k in
+                        ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
+        self._ck(lib().sr_recognise_batch_dev(self._h, _p(pcm_ptr), U, B, n_len, C.byref(ro)))
+
+
+# ---- synthetic workload (include/sr_synth.h) -------------------------------------------------------
+def synth_pcm_host(B, U, seed_base, nwords=1):
+    pcm = np.zeros((B, U), np.uint16)
+    rc = lib().sr_synth_pcm_host(_p(pcm), U, B, seed_base, nwords)
+    if rc != 0:
+        raise SrError("sr_synth_pcm_host failed")
+    return pcm
+
+
+def synth_pcm_dev(pcm_ptr, B, U, seed_base, nwords=1, stream_ptr=None):
+    rc = lib().sr_synth_pcm_dev(_p(pcm_ptr), U, B, seed_base, nwords, _p(stream_ptr))
+    if rc != 0:
+        raise SrError("sr_synth_pcm_dev failed")
+
+
+def synth_ftr_host(B, seed_base, fmin=50, fmax=100, stride=FTR_BYTES):
+    buf = np.zeros((B, stride), np.uint8)
+    rc = lib().sr_synth_ftr_host(_p(buf), stride, B, seed_base, fmin, fmax)
+    if rc != 0:
+        raise SrError("sr_synth_ftr_host failed")
+    return buf
+
+
+def make_bank(ftr, slot_stride=4096, valid=None):
+    """Pack feature structs into flash-layout slots (Src/BSP/Flash.H:11-20, Flash.C:41-63): save_sign =
+    save_mask, frm_num, rows; the rest of the slot stays erased-flash 0xFF."""
+    T = ftr.shape[0]
+    bank = np.full((T, slot_stride), 0xFF, np.uint8)
+    raw = ftr.view(np.uint8).reshape(T, FTR_BYTES)
+    for t in range(T):
+        n = int(ftr["frm_num"][t])
+        bank[t, 2:4 + 24 * n] = raw[t, 2:4 + 24 * n]
+        sign = SAVE_MASK if (valid is None or valid[t]) else 0xFFFF
+        bank[t, 0] = sign & 0xFF
+        bank[t, 1] = sign >> 8
+    return bank

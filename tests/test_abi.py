@@ -1,0 +1,69 @@
+"""The drop-in boundary without a GPU: libspeech_b200.so loads, exports every symbol that include/*.h
+declares, keeps the reference's struct layouts, and FAILS LOUDLY (no CPU fallback) when no device exists."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sr_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = "\n".join(l for l in text.split("\n") if not l.strip().startswith("#"))
+    text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    names = []
+    for stmt in text.split(";"):
+        stmt = stmt.replace('extern "C" {', "").strip()
+        if "(" in stmt and not stmt.startswith("typedef"):
+            m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*\(", stmt)
+            if m:
+                names.append(m.group(1))
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported():
+    L = sr_b200.lib()
+    names = _declared("speech_recog.h") + _declared("sr_synth.h")
+    assert {"noise_atap", "VAD", "get_mfcc", "dtw", "fft", "get_dis", "sr_recognise_batch", "sr_mfcc_batch_dev"} <= set(names)
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_struct_layouts_match_reference_headers():
+    assert sr_b200.ATAP_DTYPE.itemsize == 12               # VAD.H:10-16
+    assert sr_b200.FTR_DTYPE.itemsize == 2860              # MFCC.H:18-25 (#pragma pack(1))
+    assert sr_b200.FTR_DTYPE.fields["mfcc_dat"][1] == 4
+    assert C.sizeof(sr_b200.ValidTag) == 2 * C.sizeof(C.c_void_p)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = sr_b200.lib()
+    assert L.sr_device_count() == 0
+    with pytest.raises(sr_b200.SrError):
+        sr_b200.Handle(0)
+    assert b"no CUDA device" in L.sr_last_error(None) or len(L.sr_last_error(None)) > 0
+    # reference-named entry points return their failure sentinels
+    a = np.zeros(12, np.int16)
+    assert L.get_dis(a.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p)) == 0xFFFFFFFF
+    f = np.zeros(2, sr_b200.FTR_DTYPE)
+    assert L.dtw(f[0:1].ctypes.data_as(C.c_void_p), f[1:2].ctypes.data_as(C.c_void_p)) == 0xFFFFFFFF
+    assert not L.fft(a.ctypes.data_as(C.c_void_p), 12)
+
+
+def test_host_synth_is_deterministic_and_in_range():
+    a = sr_b200.synth_pcm_host(5, 8000, 123)
+    b = sr_b200.synth_pcm_host(5, 8000, 123)
+    c = sr_b200.synth_pcm_host(5, 8000, 124)
+    assert np.array_equal(a, b) and np.array_equal(a[1:], c[:4]) and a.max() <= 4095
+    # calibration window is noise only: |x - mid| <= 60
+    mid = np.median(a[:, :2400], axis=1)
+    assert (np.abs(a[:, :2400].astype(np.int64) - mid[:, None]) <= 61).all()

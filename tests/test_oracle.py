@@ -1,0 +1,112 @@
+"""The oracle restatement (oracle/sr_oracle.c) pinned against (a) the golden vectors produced by executing
+the reference's own C (tests/golden/golden.npz, made by tests/golden/make_golden.py) and (b) when the
+prebuilt oracle/_ref/libref.so is present, the reference itself on random / synthetic inputs. CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+import sr_b200
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CAPS = np.load(os.path.join(HERE, "golden", "captures.npz"))
+GOLD = np.load(os.path.join(HERE, "golden", "golden.npz"))
+need_ref = pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref/libref.so not built")
+
+
+@pytest.mark.parametrize("name", ["stm32_123", "stm32_456", "stm32_noise", "stm32_voice_123", "v1"])
+def test_port_matches_golden_on_board_captures(name):
+    o = ob.port()
+    pcm = CAPS[name]
+    atap = o.noise_atap(pcm, 2400)
+    assert atap.tobytes() == GOLD[name + "/atap"].tobytes()
+    seg = o.vad(pcm, len(pcm), atap)
+    assert seg.tolist() == GOLD[name + "/seg"].tolist()
+    ftrs = []
+    for k in range(3):
+        key = "%s/ftr%d" % (name, k)
+        if key in GOLD:
+            f = o.mfcc_batch(pcm.reshape(1, -1), seg[2 * k:2 * k + 2].reshape(1, 2), atap)
+            assert ob.ftr_equal(f, GOLD[key])
+            ftrs.append(f)
+    if name + "/dtw" in GOLD:
+        bank = np.concatenate(ftrs).view(np.uint8).reshape(len(ftrs), -1)
+        sc, _ = o.dtw_batch(np.concatenate(ftrs), bank, len(ftrs), 2860)
+        assert sc.tolist() == GOLD[name + "/dtw"].tolist()
+
+
+def test_port_matches_golden_on_synthetic_batch():
+    o = ob.port()
+    pcm = sr_b200.synth_pcm_host(24, 8000, 0x5EED0000)
+    tpl = sr_b200.synth_pcm_host(8, 8000, 0x7E3A0000)
+    assert [int(pcm.astype(np.uint64).sum()), int(tpl.astype(np.uint64).sum())] == GOLD["synth/pcm_sum"].tolist()
+    bank = GOLD["synth/bank"]
+    out = o.recognise_batch(pcm, 2400, bank, 8, 4096, nthreads=4)
+    for k in ("seg_off", "score", "best_idx", "best_dis", "cmd", "status"):
+        assert np.array_equal(out[k], GOLD["synth/" + k]), k
+    assert ob.ftr_equal(out["ftr"], GOLD["synth/ftr"])
+    pcm5 = sr_b200.synth_pcm_host(4, 40000, 0x5EED5000, 3)
+    out5 = o.recognise_batch(pcm5, 2400, bank, 8, 4096)
+    for k in ("seg_off", "score", "best_idx", "best_dis", "cmd", "status"):
+        assert np.array_equal(out5[k], GOLD["synth5/" + k]), k
+    assert (out5["seg_off"].reshape(4, 6) != ob.NULL).all()        # exactly max_vc_con words found
+
+
+@need_ref
+def test_port_fft_equals_reference_build_on_random_inputs():
+    rng = np.random.default_rng(11)
+    x = rng.integers(0, 2 ** 32, (64, 1024), dtype=np.uint32)           # arbitrary complex s16 pairs
+    x[:8] = 0
+    x[8:16, :160] = rng.integers(-32768, 32768, (8, 160)).astype(np.int16).astype(np.uint16)
+    assert np.array_equal(ob.port().fft_raw(x), ob.ref().fft_raw(x))
+    fr = rng.integers(-32768, 32768, (32, 160)).astype(np.int16)
+    assert np.array_equal(ob.port().fft_mag(fr), ob.ref().fft_mag(fr))
+
+
+@need_ref
+def test_port_equals_reference_build_on_noisy_and_extreme_pcm():
+    rng = np.random.default_rng(5)
+    B, U = 12, 8000
+    pcm = sr_b200.synth_pcm_host(B, U, 0xABCD0000)
+    pcm[0] = rng.integers(0, 4096, U)                 # white noise, full scale
+    pcm[1] = rng.integers(0, 65536, U)                # beyond 12 bit: exercises the s16 / u32 wraps
+    pcm[2, :] = 2048                                  # dead silent: n_thl = 0
+    pcm[3, 2400:] = np.where(np.arange(U - 2400) % 2 == 0, 0, 4095)    # maximal zero-crossing rate
+    pcm[4, 3000:7900] = rng.integers(0, 4096, 4900)  # speech runs into the end: segment never closes
+    tpl = sr_b200.synth_pcm_host(6, U, 0x7E3A0000)
+    r, p = ob.ref(), ob.port()
+    e = r.recognise_batch(tpl, 2400, None, 0, 4096)
+    bank = sr_b200.make_bank(e["ftr"], valid=[1, 1, 0, 1, 1, 1])
+    a, b = r.recognise_batch(pcm, 2400, bank, 6, 4096), p.recognise_batch(pcm, 2400, bank, 6, 4096, nthreads=3)
+    for k in ("seg_off", "score", "best_idx", "best_dis", "cmd", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert ob.ftr_equal(a["ftr"], b["ftr"])
+    # fixed-segment MFCC on the extreme rows (VAD bypassed)
+    seg = np.tile(np.array([80, 8000], np.uint32), (B, 1))
+    atap = np.zeros(B, ob.ATAP_DTYPE)
+    atap["mid_val"] = 2048
+    assert ob.ftr_equal(r.mfcc_batch(pcm, seg, atap), p.mfcc_batch(pcm, seg, atap, nthreads=2))
+
+
+@need_ref
+def test_port_dtw_equals_reference_build_on_random_features():
+    raw = sr_b200.synth_ftr_host(40, 0xD7A00000, 1, 119)
+    ftr = raw.view(ob.FTR_DTYPE).reshape(-1)
+    bank = sr_b200.synth_ftr_host(23, 0xD7A10000, 1, 119, stride=4096)
+    a, _ = ob.ref().dtw_batch(ftr, bank, 23, 4096)
+    b, cells = ob.port().dtw_batch(ftr, bank, 23, 4096, nthreads=2)
+    assert np.array_equal(a, b) and cells > 0
+    assert (a == ob.NULL).any() and (a != ob.NULL).any()          # the 2:1 guard fires on some pairs
+
+
+def test_dtw_band_oracle_properties():
+    """dtw_band is our own extension (parity unpinned by the reference): sanity properties only"""
+    raw = sr_b200.synth_ftr_host(6, 0xD7A20000, 50, 100)
+    ftr = raw.view(ob.FTR_DTYPE).reshape(-1)
+    o = ob.port()
+    sc, cells = o.dtw_batch(ftr, raw, 6, 2860, band_r=10)
+    assert (np.diag(sc) == 0).all() and cells > 0
+    wide, _ = o.dtw_batch(ftr, raw, 6, 2860, band_r=200)
+    ok = (sc != ob.NULL) & (wide != ob.NULL)
+    assert (wide[ok] <= sc[ok]).all()                               # a wider band can only lower the DP optimum
