@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py -- the reference's VAD -> MFCC -> DTW hot path (spch_recg, Src/APP/main.c:249-296) on B200.
+
+One "step" = one pass of the whole path (noise_atap + VAD + get_mfcc + dtw x T + argmin) over one batch of
+synthetic utterances (BASELINE.json configs[1]: 65 536 x 1 s utterances, 12 MFCC, 20 templates, per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          one JSON line (rank 0)
+  python bench.py --impl reference ...                         the reference's own C on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...            one rank per GPU, utterances sharded (weak
+                                                               scaling), one NCCL all-gather of the scores
+
+`value`  : utterances/s, whole job, inputs resident in HBM (device-pointer C-ABI, CUDA events, max over ranks)
+`e2e`    : the same metric through the host-buffer C-ABI call sr_recognise_batch (pinned host PCM in,
+           command index + match distance + status out; H2D and D2H inside the timed region)
+`roofline`: the dominant kernel (mfcc_kernel), algorithmic bytes (2*U_seg + 24*F + 4 per
+           utterance) / its event-timed duration inside the timed steps, vs the measured HBM peak
+`cpu_baseline`: oracle/_ref/libref.so (the reference's own C, one process per core) -- or the oracle port --
+           on a bounded sample of the same batch, timed on this box's host cores; the sample doubles as a
+           bit-exact parity check of the GPU results.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "stm32-speech-recognition_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+U = 8000                 # 1 s @ 8 kHz
+N_LEN = 2400             # 300 ms noise window (ADC.H:10-11)
+SEED = 0x5EED0000
+TPL_SEED = 0x7E3A0000
+TAGS = {0: "vad", 1: "mfcc", 2: "status", 3: "best_init", 4: "dtw", 5: "best_final", 6: "dtw_band"}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_time(pcm_sample, bank, T, cores, want_outputs=True):
+    """Run the reference's C (libref.so, one PROCESS per core: it keeps statics) or the oracle port (threads)
+    over pcm_sample; returns (seconds = slowest worker, kind, outputs or None)."""
+    import oracle_bind as ob
+    S = pcm_sample.shape[0]
+    if ob.have_ref():
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        bounds = [(S * k // cores, S * (k + 1) // cores) for k in range(cores)]
+        with ctx.Pool(cores, initializer=_ref_init, initargs=(pcm_sample, bank, T)) as pool:
+            pool.map(_ref_warm, range(cores))
+            res = pool.map(_ref_work, bounds)
+        secs = max(r[0] for r in res)
+        out = None
+        if want_outputs:
+            out = {k: np.concatenate([r[1][k] for r in res]) for k in res[0][1]}
+        return secs, "reference", out
+    o = ob.port()
+    o.recognise_batch(pcm_sample[: min(S, 64)], N_LEN, bank, T, 4096, nthreads=cores)
+    t0 = time.perf_counter()
+    out = o.recognise_batch(pcm_sample, N_LEN, bank, T, 4096, nthreads=cores)
+    return time.perf_counter() - t0, "port", out
+
+
+_G = {}
+
+
+def _ref_init(pcm, bank, T):
+    import oracle_bind as ob
+    _G["o"], _G["pcm"], _G["bank"], _G["T"] = ob.ref(), pcm, bank, T
+
+
+def _ref_warm(_):
+    _G["o"].recognise_batch(_G["pcm"][:16], N_LEN, _G["bank"], _G["T"], 4096)
+    return 0
+
+
+def _ref_work(b):
+    lo, hi = b
+    x = np.ascontiguousarray(_G["pcm"][lo:hi])
+    t0 = time.perf_counter()
+    out = _G["o"].recognise_batch(x, N_LEN, _G["bank"], _G["T"], 4096)
+    dt = time.perf_counter() - t0
+    keep = {k: out[k] for k in ("seg_off", "best_idx", "best_dis", "cmd", "status", "score")}
+    keep["frames"] = out["ftr"]["frm_num"].astype(np.uint32)
+    return dt, keep
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation on this box's host cores"""
+    if rank != 0:
+        return
+    import sr_b200
+    import oracle_bind as ob
+    cores = os.cpu_count() or 1
+    T = args.templates
+    S = min(args.batch, args.cpu_sample_per_core * cores)
+    pcm = sr_b200.synth_pcm_host(S, U, SEED)
+    tpl = sr_b200.synth_pcm_host(T, U, TPL_SEED)
+    e = ob.best_oracle().recognise_batch(tpl, N_LEN, None, 0, 4096)
+    bank = sr_b200.make_bank(e["ftr"])
+    for _ in range(args.warmup):
+        cpu_reference_time(pcm[: max(cores * 32, 64)], bank, T, cores, False)
+    secs, frames, kind = [], 0, "port"
+    for _ in range(args.steps):
+        s, kind, out = cpu_reference_time(pcm, bank, T, cores, True)
+        secs.append(s)
+        frames = int(out["frames"].sum()) if "frames" in out else int(out["ftr"]["frm_num"].sum())
+    ms = 1e3 * float(np.mean(secs))
+    val = S / (ms / 1e3)
+    sample = "first %d of %d utterances per step, %d processes" % (S, args.batch, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "utterances/s", "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 fixed-point (s16 FFT, u32 energies)", "data": "synthetic",
+        "config": {"workload": "configs[1]: 65536 x 1 s utterances, 12 MFCC, %d templates; CPU arm times a bounded sample" % T,
+                   "utterances_per_step": S, "samples_per_utterance": U, "templates": T},
+        "mfcc_frames_per_s": frames / (ms / 1e3),
+        "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="utterances per GPU per step")
+    ap.add_argument("--templates", type=int, default=20)
+    ap.add_argument("--cpu-sample-per-core", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sr_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch, args.templates
+    stream = torch.cuda.current_stream(dev)
+    h = sr_b200.Handle(local)
+    h.set_stream(stream.cuda_stream)
+
+    # ---- synthetic inputs, generated on the device (byte-identical to the host generator) ----------
+    pcm = torch.empty((B, U), dtype=torch.int16, device=dev)
+    sr_b200.synth_pcm_dev(pcm.data_ptr(), B, U, SEED + rank * B, 1, stream.cuda_stream)
+    tpl = torch.empty((T, U), dtype=torch.int16, device=dev)
+    sr_b200.synth_pcm_dev(tpl.data_ptr(), T, U, TPL_SEED, 1, stream.cuda_stream)
+    # ---- enrolment (save_mdl, main.c:121-138): template features -> flash-layout bank ---------------
+    tftr = torch.zeros((T, 2860), dtype=torch.uint8, device=dev)
+    h.set_bank_dev(0, 0, 4096)
+    h.recognise_dev(tpl.data_ptr(), U, T, N_LEN, ftr=tftr.data_ptr())
+    bank = torch.full((T, 4096), 255, dtype=torch.uint8, device=dev)
+    bank[:, :2860] = tftr
+    bank[:, 0], bank[:, 1] = 12345 & 0xFF, 12345 >> 8
+    h.set_bank_dev(bank.data_ptr(), T, 4096)
+    # ---- outputs ---------------------------------------------------------------------------------------
+    seg = torch.zeros((B, 6), dtype=torch.int32, device=dev)
+    ftr = torch.zeros((B, 2860), dtype=torch.uint8, device=dev)
+    score = torch.zeros((B, T), dtype=torch.int32, device=dev)
+    bidx = torch.zeros(B, dtype=torch.int32, device=dev)
+    bdis = torch.zeros(B, dtype=torch.int32, device=dev)
+    cmd = torch.zeros(B, dtype=torch.int32, device=dev)
+    status = torch.zeros(B, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros((world * B, T), dtype=torch.int32, device=dev) if world > 1 else None
+    outs = dict(seg_off=seg.data_ptr(), ftr=ftr.data_ptr(), score=score.data_ptr(), best_idx=bidx.data_ptr(),
+                best_dis=bdis.data_ptr(), cmd=cmd.data_ptr(), status=status.data_ptr())
+
+    def step():
+        h.recognise_dev(pcm.data_ptr(), U, B, N_LEN, **outs)
+        if world > 1:                                   # the one exchange step of the path
+            dist.all_gather_into_tensor(gathered, score)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = h.launch_count()
+    h.timing_enable(8 * args.steps + 8)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.launch_count() - launches0
+    recs = h.timing_collect()
+    h.timing_enable(0)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # ---- per-utterance statistics of this rank's shard -------------------------------------------------
+    frames_t = (ftr[:, 2].to(torch.int64) | (ftr[:, 3].to(torch.int64) << 8))
+    seg64 = seg.to(torch.int64) & 0xFFFFFFFF
+    ok = status == 0
+    stats = torch.stack([frames_t.sum(), ok.sum(), ((seg64[:, 1] - seg64[:, 0]) * ok).sum()]).to(torch.float64)
+    if world > 1:
+        dist.all_reduce(stats)
+    frames_total, ok_total, seg_samples = (float(x) for x in stats.tolist())
+
+    # ---- e2e: host-buffer C-ABI call (pinned PCM in, cmd/dis/idx/status out) --------------------------
+    pin = torch.empty((B, U), dtype=torch.int16).pin_memory()
+    pin.copy_(pcm)
+    o_cmd, o_dis = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+    o_idx, o_st = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory()
+    he = sr_b200.Handle(local)
+    he.set_bank_dev(bank.data_ptr(), T, 4096)
+    ro = sr_b200.RecogOut(None, None, None, None, o_idx.data_ptr(), o_dis.data_ptr(), o_cmd.data_ptr(), o_st.data_ptr())
+
+    def e2e_step():
+        rc = sr_b200.lib().sr_recognise_batch(he._h, C.c_void_p(pin.data_ptr()), U, B, N_LEN, C.byref(ro))
+        if rc != 0:
+            raise RuntimeError(sr_b200.lib().sr_last_error(he._h))
+
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()                                      # synchronous: returns after D2H + stream sync
+    torch.cuda.synchronize(dev)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    e2e_equal = bool(torch.equal(o_cmd.to(dev), cmd) and torch.equal(o_dis.to(dev), bdis))
+    he.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    per = {}
+    for tag, ms in recs:
+        per.setdefault(TAGS.get(tag, str(tag)), []).append(ms)
+    kern_ms = {k: float(np.mean(v)) for k, v in per.items()}
+    share = {k: v / max(sum(kern_ms.values()), 1e-9) for k, v in kern_ms.items()}
+    frames_rank0 = float(frames_t.sum().item())
+    seg_rank0 = float((((seg64[:, 1] - seg64[:, 0]) * ok).sum()).item())
+    ok_rank0 = float(ok.sum().item())
+    mfcc_bytes = 2.0 * (seg_rank0 + ok_rank0) + 24.0 * frames_rank0 + 4.0 * B     # 2*U_seg + 24*F + 4 per utterance
+    peak, peak_src = peaks()
+    ach = mfcc_bytes / (kern_ms.get("mfcc", float("nan")) * 1e-3) / 1e9
+    # integer-issue view of the same kernel (the bit-exact FFT is INT32-issue bound, not HBM bound)
+    roofline = {"bound": "hbm", "kernel": "mfcc_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": mfcc_bytes, "kernel_ms": kern_ms.get("mfcc"),
+                "kernel_share_of_step": share.get("mfcc"),
+                "note": "bit-exact fixed-point FFT: ~2000 warp instructions/frame -> INT-issue bound by design, see DESIGN.md"}
+
+    # ---- CPU baseline on a bounded sample + parity of the GPU results on that sample ----------------------
+    cpu = None
+    parity = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        S = min(B, args.cpu_sample_per_core * cores)
+        pcm_s = pcm[:S].cpu().numpy().view(np.uint16)
+        bank_h = bank.cpu().numpy()
+        secs, kind, out = cpu_reference_time(pcm_s, bank_h, T, cores, True)
+        cpu = {"value": S / secs, "unit": "utterances/s", "cores": cores, "kind": kind,
+               "sample": "first %d utterances of rank 0's batch, %d worker %s, wall = slowest worker"
+                         % (S, cores, "processes" if kind == "reference" else "threads"),
+               "mfcc_frames_per_s": float(out["frames"].sum() if "frames" in out else out["ftr"]["frm_num"].sum()) / secs}
+        g = dict(seg_off=seg[:S].cpu().numpy().view(np.uint32).reshape(-1), best_idx=bidx[:S].cpu().numpy().view(np.uint32),
+                 best_dis=bdis[:S].cpu().numpy().view(np.uint32), cmd=cmd[:S].cpu().numpy().view(np.uint32),
+                 status=status[:S].cpu().numpy(), score=score[:S].cpu().numpy().view(np.uint32).reshape(-1))
+        parity = all(np.array_equal(g[k], np.asarray(out[k]).reshape(-1)) for k in g)
+
+    total_utts = B * world
+    line = {
+        "metric": "utterances/s", "value": total_utts / (ms_step * 1e-3), "unit": "utterances/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed-point (s16 FFT, u32 energies)", "data": "synthetic",
+        "config": {"workload": "configs[1]: 65536 x 1 s utterances (8 kHz u16), 12 MFCC, 20 templates, per GPU; "
+                               "full spch_recg path: noise_atap+VAD -> get_mfcc(seg 0) -> dtw x T -> argmin",
+                   "utterances_per_gpu": B, "samples_per_utterance": U, "templates": T, "geometry": "160/80/1024 (reference)",
+                   "l2": "inputs (1.05 GB PCM per GPU) exceed the 126 MB L2; no flush needed",
+                   "multi_gpu": "utterances sharded, one NCCL all_gather of u32 scores [B,T] per step" if world > 1 else "single GPU"},
+        "mfcc_frames_per_s": frames_total / (ms_step * 1e-3),
+        "vad_ok_fraction": ok_total / total_utts,
+        "kernel_ms": kern_ms, "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu_sample": parity,
+        "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utterances/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": B * U * 2, "d2h_bytes_per_step": B * 13, "matches_device_path": e2e_equal,
+                "call": "sr_recognise_batch (host pinned buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

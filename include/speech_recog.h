@@ -165,6 +165,13 @@ int sr_get_dis_batch(sr_handle *h, const int16_t *a, const int16_t *b, uint32_t 
  * on arbitrary complex data */
 int sr_fft_raw_batch(sr_handle *h, const uint32_t *in_packed, uint32_t n, uint32_t *out_packed);
 
+/* Per-kernel device timing: after sr_timing_enable(h, max_records) every kernel launch of this handle is
+ * bracketed by a CUDA event pair on the launching stream; sr_timing_collect synchronises the stream and
+ * returns (tag, milliseconds) per launch in issue order, then rearms. Tags: 0 noise_atap+VAD, 1 get_mfcc,
+ * 2 status, 3 best-init, 4 dtw (greedy), 5 best-final, 6 dtw (banded DP). max_records = 0 disables. */
+int sr_timing_enable(sr_handle *h, uint32_t max_records);
+int sr_timing_collect(sr_handle *h, uint32_t *tags, float *ms, uint32_t cap, uint32_t *n);
+
 /* number of kernel launches this handle has issued (bench.py reports it as gpu_launches) */
 uint64_t sr_launch_count(const sr_handle *h);
 

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 #include "sr_common.cuh"
 
 namespace srk {
@@ -47,6 +48,11 @@ struct sr_handle {
     const void *bank = nullptr;
     DevBuf bank_own;
     u32 n_slot = 0, slot_stride = 0;
+    // optional per-kernel timing (sr_timing_enable): event pairs recorded around every launch
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<uint32_t> ev_tag;
+    size_t ev_used = 0;
     // grow-only device workspaces
     DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
 };
@@ -77,6 +83,24 @@ static cudaError_t ensure(DevBuf &b, size_t bytes) {
     b.cap = want;
     return cudaSuccess;
 }
+
+// records a (start,end) event pair around one kernel launch when timing is enabled
+struct TimedLaunch {
+    sr_handle *h;
+    size_t slot = (size_t)-1;
+    TimedLaunch(sr_handle *hh, uint32_t tag) : h(hh) {
+        if (h->timing && (h->ev_used + 1) * 2 <= h->ev.size()) {
+            slot = h->ev_used++;
+            h->ev_tag[slot] = tag;
+            cudaEventRecord(h->ev[2 * slot], h->stream);
+        }
+    }
+    ~TimedLaunch() {
+        if (slot != (size_t)-1) cudaEventRecord(h->ev[2 * slot + 1], h->stream);
+    }
+};
+enum { TAG_VAD = 0, TAG_MFCC = 1, TAG_STATUS = 2, TAG_BEST_INIT = 3, TAG_DTW = 4, TAG_BEST_FINAL = 5, TAG_DTW_BAND = 6,
+       TAG_FFT = 7, TAG_GET_DIS = 8 };
 
 struct DeviceGuard {
     int prev = -1;
@@ -137,6 +161,7 @@ int sr_destroy(sr_handle *h) {
     DevBuf *bufs[] = {&h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
                       &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -164,6 +189,37 @@ void *sr_host_alloc(size_t bytes) {
 }
 void sr_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// ---- per-kernel timing: event pairs on the launching stream around every kernel -----------------------
+int sr_timing_enable(sr_handle *h, uint32_t max_records) {
+    SR_REQUIRE(h, h != nullptr);
+    DeviceGuard g(h->device);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    h->ev.clear(); h->ev_tag.clear(); h->ev_used = 0;
+    h->timing = max_records > 0;
+    for (uint32_t i = 0; i < 2 * max_records; ++i) {
+        cudaEvent_t e;
+        SR_CK(h, cudaEventCreate(&e));
+        h->ev.push_back(e);
+    }
+    h->ev_tag.assign(max_records, 0);
+    return 0;
+}
+int sr_timing_collect(sr_handle *h, uint32_t *tags, float *ms, uint32_t cap, uint32_t *n) {
+    SR_REQUIRE(h, h && n);
+    DeviceGuard g(h->device);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    uint32_t k = 0;
+    for (size_t i = 0; i < h->ev_used && k < cap; ++i, ++k) {
+        float t = 0.f;
+        SR_CK(h, cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
+        if (tags) tags[k] = h->ev_tag[i];
+        if (ms) ms[k] = t;
+    }
+    *n = k;
+    h->ev_used = 0;
+    return 0;
+}
+
 // ---- template bank --------------------------------------------------------------------------------
 int sr_set_bank_dev(sr_handle *h, const void *bank_dev, uint32_t n_slot, uint32_t slot_stride) {
     SR_REQUIRE(h, h != nullptr);
@@ -190,7 +246,7 @@ int sr_noise_atap_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint3
     SR_REQUIRE(h, h && (B == 0 || (pcm && atap)));
     SR_REQUIRE(h, U <= 65535u && n_len <= 65535u);
     DeviceGuard g(h->device);
-    SR_CK(h, launch_vad(pcm, U, B, n_len, 0, 1, 0, atap, nullptr, h->num_sms, h->stream));
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, 0, 1, 0, atap, nullptr, h->num_sms, h->stream)); }
     h->launches += B ? 1 : 0;
     return 0;
 }
@@ -200,7 +256,7 @@ int sr_vad_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, 
     SR_REQUIRE(h, h && (B == 0 || (pcm && atap && seg_off)));
     SR_REQUIRE(h, U <= 65535u && buf_len <= U);
     DeviceGuard g(h->device);
-    SR_CK(h, launch_vad(pcm, U, B, 0, buf_len, 0, 1, const_cast<atap_tag *>(atap), seg_off, h->num_sms, h->stream));
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, 0, buf_len, 0, 1, const_cast<atap_tag *>(atap), seg_off, h->num_sms, h->stream)); }
     h->launches += B ? 1 : 0;
     return 0;
 }
@@ -210,7 +266,7 @@ int sr_mfcc_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B,
     SR_REQUIRE(h, h && (B == 0 || (pcm && seg && atap && ftr)));
     SR_REQUIRE(h, seg_stride >= 2 && (reinterpret_cast<uintptr_t>(ftr) & 3) == 0);
     DeviceGuard g(h->device);
-    SR_CK(h, launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream));
+    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream)); }
     h->launches += B ? 1 : 0;
     return 0;
 }
@@ -225,20 +281,22 @@ static int dtw_dev_impl(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t 
     if (want_best) {
         SR_CK(h, ensure(h->best, (size_t)B * 8));
         best = static_cast<u64 *>(h->best.p);
-        SR_CK(h, launch_best_init(best, B, h->stream));
+        { TimedLaunch tl(h, TAG_BEST_INIT); SR_CK(h, launch_best_init(best, B, h->stream)); }
         ++h->launches;
     }
     if (h->n_slot) {
         if (flags & SR_DTW_BAND) {
             SR_REQUIRE(h, band_r >= 0);
+            TimedLaunch tl(h, TAG_DTW_BAND);
             SR_CK(h, launch_dtw_band(in, B, h->bank, h->n_slot, h->slot_stride, flags, band_r, score, best, h->num_sms, h->stream));
         } else {
+            TimedLaunch tl(h, TAG_DTW);
             SR_CK(h, launch_dtw(in, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream));
         }
         ++h->launches;
     }
     if (want_best) {
-        SR_CK(h, launch_best_final(best, B, best_idx, best_dis, cmd, status, h->stream));
+        { TimedLaunch tl(h, TAG_BEST_FINAL); SR_CK(h, launch_best_final(best, B, best_idx, best_dis, cmd, status, h->stream)); }
         ++h->launches;
     }
     return 0;
@@ -270,10 +328,10 @@ int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32
     u8 *status = o->status;
     if (!status) { SR_CK(h, ensure(h->status, (size_t)B)); status = static_cast<u8 *>(h->status.p); }
     // main.c:258-260 noise_atap + VAD (one fused launch on the staged utterance)
-    SR_CK(h, launch_vad(pcm, U, B, n_len, U, 1, 1, atap, seg, h->num_sms, h->stream));
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, U, 1, 1, atap, seg, h->num_sms, h->stream)); }
     // main.c:268 get_mfcc of segment 0
-    SR_CK(h, launch_mfcc(pcm, U, B, seg, 6, atap, ftr, h->num_sms, h->stream));
-    SR_CK(h, launch_status(seg, ftr, B, status, h->stream));
+    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc(pcm, U, B, seg, 6, atap, ftr, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_STATUS); SR_CK(h, launch_status(seg, ftr, B, status, h->stream)); }
     h->launches += 3;
     // main.c:276-294 template scan, argmin, command index
     return dtw_dev_impl(h, ftr, B, SR_DTW_CHECK_SIGN, 0, o->score, o->best_idx, o->best_dis, o->cmd, status);

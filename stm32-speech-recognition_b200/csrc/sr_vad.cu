@@ -216,7 +216,7 @@ cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int
     if (warps < 1) return cudaErrorInvalidValue;
     if (warps > kVadMaxWarps) warps = kVadMaxWarps;
     const size_t smem = per_warp * warps;
-    cudaError_t e = cudaFuncSetAttribute(vad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(vad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);   // + 96 B static barriers <= 227 KB
     if (e != cudaSuccess) return e;
     u32 grid = (B + warps - 1) / warps;
     const u32 cap = (u32)num_sms * 4;

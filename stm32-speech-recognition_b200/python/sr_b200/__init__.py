@@ -56,6 +56,8 @@ def lib():
         L.sr_host_free.argtypes = [vp]
         L.sr_launch_count.argtypes = [vp]
         L.sr_launch_count.restype = u64
+        L.sr_timing_enable.argtypes = [vp, u32]
+        L.sr_timing_collect.argtypes = [vp, vp, vp, u32, vp]
         L.sr_set_bank.argtypes = [vp, vp, u32, u32]
         L.sr_set_bank_dev.argtypes = [vp, vp, u32, u32]
         for name in ("sr_noise_atap_batch", "sr_noise_atap_batch_dev"):
@@ -138,6 +140,17 @@ class Handle:
 
     def launch_count(self):
         return int(lib().sr_launch_count(self._h))
+
+    def timing_enable(self, max_records):
+        self._ck(lib().sr_timing_enable(self._h, max_records))
+        self._timing_cap = max_records
+
+    def timing_collect(self):
+        """[(tag, ms), ...] for every kernel launched since the last collect (synchronises the stream)"""
+        cap = getattr(self, "_timing_cap", 0)
+        tags, ms, n = np.zeros(cap, np.uint32), np.zeros(cap, np.float32), C.c_uint32(0)
+        self._ck(lib().sr_timing_collect(self._h, _p(tags), _p(ms), cap, C.byref(n)))
+        return list(zip(tags[: n.value].tolist(), ms[: n.value].tolist()))
 
     def set_bank(self, bank, n_slot, slot_stride):
         self._ck(lib().sr_set_bank(self._h, _p(bank), n_slot, slot_stride))

@@ -1,0 +1,383 @@
+"""GPU parity tests proper: every call goes through the C-ABI of libspeech_b200.so and is compared
+BIT-EXACTLY (integer path: tolerance 0) with the oracle -- the reference's own C when oracle/_ref/libref.so
+travelled with the repo, else the restatement -- and with the committed golden vectors."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+import sr_b200
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CAPS = np.load(os.path.join(HERE, "golden", "captures.npz"))
+GOLD = np.load(os.path.join(HERE, "golden", "golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def ora():
+    return ob.best_oracle()
+
+
+def _cmp_recog(out, ref, keys=("seg_off", "score", "best_idx", "best_dis", "cmd", "status")):
+    for k in keys:
+        assert np.array_equal(out[k].reshape(-1), ref[k].reshape(-1)), k
+    assert ob.ftr_equal(out["ftr"], ref["ftr"])
+
+
+# ---- FFT: the asm restatement on device, arbitrary complex inputs -----------------------------------
+def test_fft_raw_bit_exact(handle, ora):
+    rng = np.random.default_rng(21)
+    x = rng.integers(0, 2 ** 32, (96, 1024), dtype=np.uint32)
+    x[:4] = 0
+    x[4:8] = 0x7FFF7FFF
+    x[8:12] = 0x80008000                               # -32768 everywhere: pw = 2^31 corner of MFCC.C:56
+    x[12:44, :] = rng.integers(-3000, 3000, (32, 1024)).astype(np.int16).astype(np.uint16)
+    assert np.array_equal(handle.fft_raw(x), ora.fft_raw(x))
+
+
+@pytest.mark.parametrize("length", [0, 1, 160, 161, 256, 1000, 1024])
+def test_fft_mag_bit_exact(handle, ora, length):
+    rng = np.random.default_rng(length)
+    fr = np.ascontiguousarray(rng.integers(-32768, 32768, (16, max(length, 1))).astype(np.int16)[:, :length])
+    want = ora.fft_mag(fr) if length else np.zeros((16, 512), np.uint32)      # all-zero input -> all-zero spectrum
+    assert np.array_equal(handle.fft_mag(fr), want)
+
+
+# ---- get_mfcc ----------------------------------------------------------------------------------------
+def test_mfcc_fixed_segment_config2_shape(handle, ora):
+    """BASELINE config 2 geometry: segment [80, 8000) of every utterance, mid = 2048 -> 98 frames"""
+    B, U = 96, 8000
+    pcm = sr_b200.synth_pcm_host(B, U, 0x5EED0000)
+    seg = np.tile(np.array([80, 8000], np.uint32), (B, 1))
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = 2048
+    got = handle.mfcc(pcm, seg, atap)
+    assert (got["frm_num"] == 98).all()
+    assert ob.ftr_equal(got, ora.mfcc_batch(pcm, seg, atap))
+
+
+def test_mfcc_extreme_inputs_and_ragged_segments(handle, ora):
+    rng = np.random.default_rng(9)
+    B, U = 64, 12000
+    pcm = rng.integers(0, 4096, (B, U)).astype(np.uint16)
+    pcm[:8] = rng.integers(0, 65536, (8, U))           # > 12 bit: s16 window wrap, u32 energy wrap
+    pcm[8] = 0
+    pcm[9] = 65535
+    pcm[10] = 2048                                     # all-zero frames: filter sums 0 -> log(0) pinned to 0
+    starts = rng.integers(1, 4000, B) // 1 * 1
+    lens = rng.integers(0, 130, B) * 80 + rng.integers(0, 80, B)      # ragged, some < 160, some > 119 frames
+    ends = np.minimum(starts + lens, U)
+    seg = np.stack([starts, ends], 1).astype(np.uint32)
+    seg[11] = [ob.NULL, ob.NULL]
+    seg[12] = [100, ob.NULL]
+    seg[13] = [80, 80 + 160]                           # exactly one frame
+    seg[14] = [80, 80 + 118 * 80 + 160]               # exactly vv_frm_max = 119 frames
+    seg[16] = [80, 80 + 119 * 80 + 160]               # 120 frames: rejected, frm_num = 0 (MFCC.C:103-107)
+    seg[15] = [1, 1 + 159]                             # one sample short of a frame
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = rng.integers(0, 4096, B)
+    got = handle.mfcc(pcm, seg, atap)
+    valid = (seg[:, 0] != ob.NULL) & (seg[:, 1] != ob.NULL)
+    want = ora.mfcc_batch(pcm[valid], seg[valid], atap[valid])
+    assert ob.ftr_equal(got[valid], want)
+    assert (got["frm_num"][~valid] == 0).all()
+    assert (got["frm_num"] == 0).any() and (got["frm_num"] > 100).any() and (got["frm_num"] == 1).any()
+
+
+@pytest.mark.parametrize("U", [8000, 8003, 5001, 16000])
+def test_mfcc_unaligned_utterance_stride(handle, ora, U):
+    """utterance strides that break the 16-byte phase of the bulk copies; last utterance ends at the buffer end"""
+    B = 37
+    pcm = sr_b200.synth_pcm_host(B, U, 0x77 + U)
+    rng = np.random.default_rng(U)
+    st = rng.integers(1, 900, B)
+    en = np.minimum(st + rng.integers(160, 4000, B), U)
+    en[-1] = U
+    st[0] = 1
+    seg = np.stack([st, en], 1).astype(np.uint32)
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = 2000
+    assert ob.ftr_equal(handle.mfcc(pcm, seg, atap), ora.mfcc_batch(pcm, seg, atap))
+
+
+def test_mfcc_segment_at_sample_zero_reads_previous_utterance(handle, ora):
+    """start == 0 makes MFCC.C:119 read vc_dat[-1]; for b > 0 that is the last sample of utterance b-1 in a
+    contiguous batch (same as the reference on the same memory); for b == 0 it is pinned to mid_val."""
+    B, U = 5, 4000
+    pcm = sr_b200.synth_pcm_host(B, U, 0x99)
+    seg = np.tile(np.array([0, 1600], np.uint32), (B, 1))
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = 2100
+    got = handle.mfcc(pcm, seg, atap)
+    # oracle on a buffer with one leading sample = mid_val: utterance 0 then sees x[-1] = mid
+    flat = np.concatenate([[np.uint16(2100)], pcm.reshape(-1)])
+    for b in range(B):
+        view = flat[b * U: b * U + 1 + U].copy().reshape(1, -1)
+        want = ora.mfcc_batch(view, np.array([[1, 1601]], np.uint32), atap[b:b + 1])
+        assert ob.ftr_equal(got[b:b + 1], want), b
+
+
+# ---- noise_atap + VAD ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["stm32_123", "stm32_456", "stm32_noise", "stm32_voice_123", "v1"])
+def test_vad_on_board_captures_matches_golden(handle, name):
+    pcm = CAPS[name].reshape(1, -1)
+    atap = handle.noise_atap(pcm, 2400)
+    assert atap.tobytes() == GOLD[name + "/atap"].tobytes()
+    seg = handle.vad(pcm, atap)
+    assert seg.reshape(-1).tolist() == GOLD[name + "/seg"].tolist()
+
+
+def test_vad_extremes_bit_exact(handle, ora):
+    rng = np.random.default_rng(4)
+    B, U = 48, 8000
+    pcm = sr_b200.synth_pcm_host(B, U, 0xABCD0000)
+    pcm[0] = rng.integers(0, 4096, U)
+    pcm[1] = rng.integers(0, 65536, U)
+    pcm[2] = 2048
+    pcm[3, 2400:] = np.where(np.arange(U - 2400) % 2 == 0, 0, 4095)
+    pcm[4, 3000:7900] = rng.integers(0, 4096, 4900)
+    for b in range(5, 16):                            # sparse out-of-band spikes: exercises the carried last_sig
+        pcm[b] = 2048 + rng.integers(-3, 4, U)
+        idx = rng.integers(2400, U, 60)
+        pcm[b, idx] = np.where(rng.integers(0, 2, 60) == 1, 2048 + 500, 2048 - 500)
+    atap = handle.noise_atap(pcm, 2400)
+    seg = handle.vad(pcm, atap)
+    for b in range(B):
+        a = ora.noise_atap(pcm[b], 2400)
+        assert a.tobytes() == atap[b:b + 1].tobytes(), b
+        assert ora.vad(pcm[b], U, a).tolist() == seg[b].reshape(-1).tolist(), b
+    # n_len not a multiple of 240 leaves atap untouched (VAD.C:33-36)
+    keep = atap.copy()
+    keep["mid_val"] = 7
+    assert handle.noise_atap(pcm, 2401, keep.copy()).tobytes() == keep.tobytes()
+
+
+@pytest.mark.parametrize("U,buf_len", [(8000, 8000), (8000, 7777), (16000, 16000), (40000, 40000), (8003, 8003), (400, 400), (160, 160)])
+def test_vad_lengths(handle, ora, U, buf_len):
+    B = 9
+    pcm = sr_b200.synth_pcm_host(B, U, 0x1234 + U, 3 if U > 20000 else 1)
+    n_len = 2400 if U >= 2400 else (240 if U >= 240 else 0)    # n_len = 0: noise_atap leaves atap untouched
+    atap0 = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap0["mid_val"], atap0["n_thl"], atap0["z_thl"], atap0["s_thl"] = 2000, 40, 2, 3000
+    atap = handle.noise_atap(pcm, n_len, atap0.copy())
+    seg = handle.vad(pcm, atap, buf_len)
+    for b in range(B):
+        a = ora.noise_atap(pcm[b], n_len, atap0[b:b + 1]) if n_len else atap0[b:b + 1].copy()
+        assert a.tobytes() == atap[b:b + 1].tobytes()
+        if buf_len > 160:
+            assert ora.vad(pcm[b], buf_len, a).tolist() == seg[b].reshape(-1).tolist(), b
+        else:
+            assert (seg[b] == ob.NULL).all()
+
+
+# ---- dtw ---------------------------------------------------------------------------------------------
+def test_dtw_all_lengths_bit_exact(handle, ora):
+    B, T = 150, 70
+    ftr = sr_b200.synth_ftr_host(B, 0xD7A00000, 1, 119).view(sr_b200.FTR_DTYPE).reshape(-1)
+    bank = sr_b200.synth_ftr_host(T, 0xD7A10000, 1, 119, stride=4096)
+    bank[5, 0] = 0                                     # save_sign != 12345
+    bank[17, :2] = 0xFF
+    handle.set_bank(bank, T, 4096)
+    want, _ = ora.dtw_batch(ftr, bank, T, 4096, check_sign=0)
+    score, bi, bd = handle.dtw(ftr, flags=0)
+    assert np.array_equal(score, want)
+    key = (want.astype(np.uint64) << np.uint64(32)) | np.arange(T, dtype=np.uint64)[None, :]
+    k = key.min(axis=1)
+    assert np.array_equal(bi, (k & np.uint64(0xFFFFFFFF)).astype(np.uint32)) and np.array_equal(bd, (k >> np.uint64(32)).astype(np.uint32))
+    want_s, _ = ora.dtw_batch(ftr, bank, T, 4096, check_sign=1)
+    score_s, _, _ = handle.dtw(ftr, flags=sr_b200.DTW_CHECK_SIGN)
+    assert np.array_equal(score_s, want_s) and (score_s[:, 5] == ob.NULL).all()
+
+
+def test_dtw_extreme_values_wrap(handle, ora):
+    """|dif| up to 65535 per dimension: the u32 accumulation of get_dis wraps (DTW.C:56)"""
+    rng = np.random.default_rng(2)
+    B, T = 40, 33
+    ftr = sr_b200.synth_ftr_host(B, 1, 30, 60).view(sr_b200.FTR_DTYPE).reshape(-1).copy()
+    ftr["mfcc_dat"] = rng.integers(-32768, 32768, ftr["mfcc_dat"].shape)
+    bank = sr_b200.synth_ftr_host(T, 2, 30, 60)
+    bank[:, 4:] = rng.integers(0, 256, bank[:, 4:].shape)
+    handle.set_bank(bank, T, 2860)
+    want, _ = ora.dtw_batch(ftr, bank, T, 2860)
+    score, _, _ = handle.dtw(ftr)
+    assert np.array_equal(score, want)
+    a = rng.integers(-32768, 32768, (500, 12)).astype(np.int16)
+    b = rng.integers(-32768, 32768, (500, 12)).astype(np.int16)
+    assert np.array_equal(handle.get_dis(a, b), ora.get_dis(a, b))
+
+
+@pytest.mark.parametrize("r", [10, 3, 15])
+def test_dtw_band_extension_vs_own_dp_oracle(handle, r):
+    """Sakoe-Chiba DP (BASELINE configs[2]); NOT in the reference -> checked against our own CPU DP (parity unpinned)"""
+    B, T = 70, 45
+    ftr = sr_b200.synth_ftr_host(B, 0xD7A00000, 1, 119).view(sr_b200.FTR_DTYPE).reshape(-1)
+    ftr2 = sr_b200.synth_ftr_host(B, 0xD7A00100, 50, 100).view(sr_b200.FTR_DTYPE).reshape(-1)
+    ftr = np.concatenate([ftr, ftr2])
+    bank = sr_b200.synth_ftr_host(T, 0xD7A10000, 40, 110, stride=4096)
+    handle.set_bank(bank, T, 4096)
+    want, cells = ob.port().dtw_batch(ftr, bank, T, 4096, band_r=r, nthreads=4)
+    score, bi, bd = handle.dtw(ftr, flags=sr_b200.DTW_BAND, band_r=r)
+    assert np.array_equal(score, want) and cells > 0
+    assert (want != ob.NULL).any() and (want == ob.NULL).any()
+    key = (want.astype(np.uint64) << np.uint64(32)) | np.arange(T, dtype=np.uint64)[None, :]
+    assert np.array_equal(bd, (key.min(axis=1) >> np.uint64(32)).astype(np.uint32))
+
+
+# ---- spch_recg ---------------------------------------------------------------------------------------
+def test_recognise_matches_golden_synthetic(handle):
+    pcm = sr_b200.synth_pcm_host(24, 8000, 0x5EED0000)
+    bank = GOLD["synth/bank"]
+    handle.set_bank(bank, 8, 4096)
+    out = handle.recognise(pcm, 2400)
+    _cmp_recog(out, {k: GOLD["synth/" + k] for k in ("seg_off", "score", "best_idx", "best_dis", "cmd", "status", "ftr")})
+    pcm5 = sr_b200.synth_pcm_host(4, 40000, 0x5EED5000, 3)
+    out5 = handle.recognise(pcm5, 2400)
+    _cmp_recog(out5, {k: GOLD["synth5/" + k] for k in ("seg_off", "score", "best_idx", "best_dis", "cmd", "status", "ftr")})
+
+
+def test_recognise_mixed_failures_vs_oracle(handle, ora):
+    rng = np.random.default_rng(6)
+    B, U, T = 200, 8000, 11
+    pcm = sr_b200.synth_pcm_host(B, U, 0xC0FFEE00)
+    pcm[3] = 2048                                     # VAD fail
+    pcm[4, 2500:7990] = rng.integers(0, 4096, 5490)   # segment never closes: VAD fail
+    pcm[7] = rng.integers(0, 4096, U)
+    tpl = sr_b200.synth_pcm_host(T, U, 0x7E3A0000)
+    handle.set_bank(np.zeros((1, 4096), np.uint8), 0, 4096)
+    e = handle.recognise(tpl, 2400, want=("ftr", "status"))
+    bank = sr_b200.make_bank(e["ftr"], valid=[1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1])
+    handle.set_bank(bank, T, 4096)
+    out = handle.recognise(pcm, 2400)
+    ref = ora.recognise_batch(pcm, 2400, bank, T, 4096)
+    _cmp_recog(out, ref)
+    assert set(out["status"].tolist()) >= {0, 1}
+    # empty bank: idx 0, dis_max (main.c:276-278)
+    handle.set_bank(bank, 0, 4096)
+    o2 = handle.recognise(pcm[:5], 2400, want=("best_idx", "best_dis", "cmd"))
+    assert (o2["best_idx"] == 0).all() and (o2["best_dis"] == ob.NULL).all()
+
+
+def test_recognise_2s_buffers_and_long_segments(handle, ora):
+    """the reference's native 2 s buffer; words long enough to exceed vv_frm_max -> MFCC fail (status 2)"""
+    B, U = 16, 16000
+    pcm = sr_b200.synth_pcm_host(B, U, 0x2222, 2)
+    rng = np.random.default_rng(8)
+    pcm[0, 3000:13500] = 2048 + (1200 * np.sin(np.arange(10500) * 0.3)).astype(np.int64) + rng.integers(-50, 50, 10500)
+    tpl = sr_b200.synth_pcm_host(4, 8000, 0x7E3A0000)
+    handle.set_bank(np.zeros((1, 4096), np.uint8), 0, 4096)
+    bank = sr_b200.make_bank(handle.recognise(tpl, 2400, want=("ftr",))["ftr"])
+    handle.set_bank(bank, 4, 4096)
+    out = handle.recognise(pcm, 2400)
+    _cmp_recog(out, ora.recognise_batch(pcm, 2400, bank, 4, 4096))
+    assert out["status"][0] == 2
+
+
+# ---- the reference's own entry points (batch of 1) -----------------------------------------------------
+def test_reference_named_entry_points(handle, ora):
+    L = sr_b200.lib()
+    pcm = CAPS["stm32_123"].copy()
+    atap = np.zeros(1, sr_b200.ATAP_DTYPE)
+    L.noise_atap(pcm.ctypes.data_as(C.c_void_p), 2400, atap.ctypes.data_as(C.c_void_p))
+    assert atap.tobytes() == GOLD["stm32_123/atap"].tobytes()
+    vv = (sr_b200.ValidTag * 3)()
+    L.VAD(pcm.ctypes.data_as(C.c_void_p), 16000, vv, atap.ctypes.data_as(C.c_void_p))
+    base = pcm.ctypes.data
+    offs = [((v.start - base) // 2 if v.start else ob.NULL, (v.end - base) // 2 if v.end else ob.NULL) for v in vv]
+    assert [x for p in offs for x in p] == GOLD["stm32_123/seg"].tolist()
+    f = np.zeros(2, sr_b200.FTR_DTYPE)
+    f["save_sign"] = 4321
+    L.get_mfcc(C.byref(vv[0]), f[0:1].ctypes.data_as(C.c_void_p), atap.ctypes.data_as(C.c_void_p))
+    L.get_mfcc(C.byref(vv[1]), f[1:2].ctypes.data_as(C.c_void_p), atap.ctypes.data_as(C.c_void_p))
+    assert ob.ftr_equal(f[0:1], GOLD["stm32_123/ftr0"]) and ob.ftr_equal(f[1:2], GOLD["stm32_123/ftr1"])
+    assert (f["save_sign"] == 4321).all()              # MFCC.C never writes save_sign
+    d01 = L.dtw(f[0:1].ctypes.data_as(C.c_void_p), f[1:2].ctypes.data_as(C.c_void_p))
+    d00 = L.dtw(f[0:1].ctypes.data_as(C.c_void_p), f[0:1].ctypes.data_as(C.c_void_p))
+    assert [[d00, d01]] == GOLD["stm32_123/dtw"][:1].tolist()
+    r0, r1 = f["mfcc_dat"][0][:12].copy(), f["mfcc_dat"][1][:12].copy()
+    assert L.get_dis(r0.ctypes.data_as(C.c_void_p), r1.ctypes.data_as(C.c_void_p)) == ora.get_dis(r0.reshape(1, 12), r1.reshape(1, 12))[0]
+    fr = (pcm[4000:4160].astype(np.int32) - 2213).astype(np.int16)
+    p = L.fft(fr.ctypes.data_as(C.c_void_p), 160)
+    mag = np.ctypeslib.as_array(p, shape=(1024,))[:512].copy()
+    assert np.array_equal(mag, ora.fft_mag(fr.reshape(1, -1))[0])
+    assert not L.fft(fr.ctypes.data_as(C.c_void_p), 1025)  # MFCC.C:32-35
+
+
+# ---- full-size, size-independent properties ------------------------------------------------------------
+def test_large_batch_shard_invariance_and_sampled_parity(handle, ora):
+    """BASELINE-size run (16 384 x 1 s here to bound host RAM/time): results do not depend on how the batch is
+    sharded (what the multi-GPU split relies on), enrolment then recognition of the same audio gives
+    distance 0 against its own template, and a random sample agrees with the oracle bit-for-bit."""
+    B, U, T = 16384, 8000, 20
+    pcm = sr_b200.synth_pcm_host(B, U, 0x5EED0000)
+    handle.set_bank(np.zeros((1, 4096), np.uint8), 0, 4096)
+    enrol = handle.recognise(pcm[:T], 2400, want=("ftr", "status"))
+    assert (enrol["status"] == 0).all()
+    bank = sr_b200.make_bank(enrol["ftr"])
+    handle.set_bank(bank, T, 4096)
+    full = handle.recognise(pcm, 2400)
+    assert (full["best_idx"][:T] == np.arange(T)).all() and (full["best_dis"][:T] == 0).all()
+    cut = 5000
+    a = handle.recognise(pcm[:cut], 2400)
+    b = handle.recognise(pcm[cut:], 2400)
+    for k in ("seg_off", "score", "best_idx", "best_dis", "cmd", "status"):
+        assert np.array_equal(full[k], np.concatenate([a[k], b[k]])), k
+    assert ob.ftr_equal(full["ftr"], np.concatenate([a["ftr"], b["ftr"]]))
+    idx = np.random.default_rng(0).choice(B, 192, replace=False)
+    ref = ora.recognise_batch(np.ascontiguousarray(pcm[idx]), 2400, bank, T, 4096)
+    _cmp_recog({k: v[idx] for k, v in full.items()}, ref)
+    assert (full["status"] == 0).mean() > 0.99
+
+
+# ---- device-pointer variants on a torch stream ----------------------------------------------------------
+def test_device_pointer_api_on_torch_stream(ora):
+    import torch
+    dev = torch.device("cuda:0")
+    B, U, T = 300, 8000, 9
+    h = sr_b200.Handle(0)
+    st = torch.cuda.Stream(dev)
+    h.set_stream(st.cuda_stream)
+    pcm_h = sr_b200.synth_pcm_host(B, U, 0x5151)
+    with torch.cuda.stream(st):
+        pcm = torch.empty((B, U), dtype=torch.int16, device=dev)
+        sr_b200.synth_pcm_dev(pcm.data_ptr(), B, U, 0x5151, 1, st.cuda_stream)     # device generator == host generator
+        tpl = torch.empty((T, U), dtype=torch.int16, device=dev)
+        sr_b200.synth_pcm_dev(tpl.data_ptr(), T, U, 0x7E3A0000, 1, st.cuda_stream)
+        ftr_t = torch.zeros((T, 2860), dtype=torch.uint8, device=dev)
+        h.set_bank_dev(0, 0, 4096)
+        h.recognise_dev(tpl.data_ptr(), U, T, 2400, ftr=ftr_t.data_ptr())
+        bank = torch.full((T, 4096), 255, dtype=torch.uint8, device=dev)
+        bank[:, :2860] = ftr_t
+        bank[:, 0] = 12345 & 0xFF
+        bank[:, 1] = 12345 >> 8
+        h.set_bank_dev(bank.data_ptr(), T, 4096)
+        score = torch.zeros((B, T), dtype=torch.int32, device=dev)
+        bidx = torch.zeros(B, dtype=torch.int32, device=dev)
+        bdis = torch.zeros(B, dtype=torch.int32, device=dev)
+        cmd = torch.zeros(B, dtype=torch.int32, device=dev)
+        status = torch.zeros(B, dtype=torch.uint8, device=dev)
+        seg = torch.zeros((B, 6), dtype=torch.int32, device=dev)
+        h.recognise_dev(pcm.data_ptr(), U, B, 2400, seg_off=seg.data_ptr(), score=score.data_ptr(),
+                        best_idx=bidx.data_ptr(), best_dis=bdis.data_ptr(), cmd=cmd.data_ptr(), status=status.data_ptr())
+    st.synchronize()
+    assert np.array_equal(pcm.cpu().numpy().view(np.uint16), pcm_h)
+    bank_h = bank.cpu().numpy()
+    ref = ora.recognise_batch(pcm_h, 2400, bank_h, T, 4096)
+    assert np.array_equal(score.cpu().numpy().view(np.uint32), ref["score"])
+    assert np.array_equal(seg.cpu().numpy().view(np.uint32).reshape(-1), ref["seg_off"].reshape(-1))
+    assert np.array_equal(bidx.cpu().numpy().view(np.uint32), ref["best_idx"])
+    assert np.array_equal(bdis.cpu().numpy().view(np.uint32), ref["best_dis"])
+    assert np.array_equal(cmd.cpu().numpy().view(np.uint32), ref["cmd"])
+    assert np.array_equal(status.cpu().numpy(), ref["status"])
+    assert h.launch_count() >= 6
+    h.close()
+
+
+def test_empty_batch_and_argument_errors(handle):
+    z = np.zeros((0, 8000), np.uint16)
+    assert handle.recognise(z, 2400)["cmd"].shape == (0,)
+    with pytest.raises(sr_b200.SrError):
+        handle.set_bank(np.zeros((2, 100), np.uint8), 2, 100)          # slot stride < sizeof(v_ftr_tag)
