@@ -40,6 +40,18 @@ TPL_SEED = 0x7E3A0000
 TAGS = {0: "vad", 1: "mfcc", 2: "status", 3: "best_init", 4: "dtw", 5: "best_final", 6: "dtw_band"}
 
 
+def usable_cores():
+    """host threads this process may actually use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -55,7 +67,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.t_mark = [], None, gpu_index, None
+
+    def mark(self):
+        """start of the timed region: samples before it (warm-up, also under load) are used only if the
+        region itself was too short to be sampled"""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -69,7 +86,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
     def stop(self):
         if not self.proc:
@@ -80,12 +97,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 8]
+        timed = [r for r in rows if self.t_mark is not None and r[0] >= self.t_mark]
+        window = "timed region"
+        if len(timed) < 3:                               # region shorter than a few 200 ms samples
+            timed, window = rows[-max(3, len(timed)):], "warm-up + timed region (timed region too short to sample)"
+        sm = [float(r[1]) for r in timed if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in timed if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in timed if r[3].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i] == "Active" for r in timed)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": reasons}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -139,33 +162,49 @@ def _ref_work(b):
 
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation on this box's host cores"""
+    """--impl reference: the reference's own CPU implementation on this box's host cores (one process per
+    core, persistent pool), each step a bounded sample of the configs[1] batch"""
     if rank != 0:
         return
     import sr_b200
     import oracle_bind as ob
-    cores = os.cpu_count() or 1
+    cores = args.ref_procs if args.ref_procs > 0 else usable_cores()
     T = args.templates
-    S = min(args.batch, args.cpu_sample_per_core * cores)
+    S = min(args.batch, max(args.ref_sample_per_core, 1) * cores)
     pcm = sr_b200.synth_pcm_host(S, U, SEED)
     tpl = sr_b200.synth_pcm_host(T, U, TPL_SEED)
     e = ob.best_oracle().recognise_batch(tpl, N_LEN, None, 0, 4096)
     bank = sr_b200.make_bank(e["ftr"])
-    for _ in range(args.warmup):
-        cpu_reference_time(pcm[: max(cores * 32, 64)], bank, T, cores, False)
-    secs, frames, kind = [], 0, "port"
-    for _ in range(args.steps):
-        s, kind, out = cpu_reference_time(pcm, bank, T, cores, True)
-        secs.append(s)
-        frames = int(out["frames"].sum()) if "frames" in out else int(out["ftr"]["frm_num"].sum())
+    secs, frames = [], 0
+    if ob.have_ref():
+        import multiprocessing as mp
+        kind = "reference"
+        bounds = [(S * k // cores, S * (k + 1) // cores) for k in range(cores)]
+        with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(pcm, bank, T)) as pool:
+            for i in range(args.warmup + args.steps):
+                res = pool.map(_ref_work, bounds, chunksize=1)
+                if i >= args.warmup:
+                    secs.append(max(r[0] for r in res))
+                    frames = int(sum(int(r[1]["frames"].sum()) for r in res))
+    else:
+        kind = "port"
+        o = ob.port()
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            out = o.recognise_batch(pcm, N_LEN, bank, T, 4096, nthreads=cores)
+            if i >= args.warmup:
+                secs.append(time.perf_counter() - t0)
+                frames = int(out["ftr"]["frm_num"].sum())
     ms = 1e3 * float(np.mean(secs))
     val = S / (ms / 1e3)
-    sample = "first %d of %d utterances per step, %d processes" % (S, args.batch, cores)
+    sample = "first %d of %d utterances per step, %d worker %s, step time = slowest worker" % (
+        S, args.batch, cores, "processes" if kind == "reference" else "threads")
     print(json.dumps({
         "impl": "reference", "metric": "utterances/s", "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32 fixed-point (s16 FFT, u32 energies)", "data": "synthetic",
-        "config": {"workload": "configs[1]: 65536 x 1 s utterances, 12 MFCC, %d templates; CPU arm times a bounded sample" % T,
+        "config": {"workload": "configs[1]: 65536 x 1 s utterances (8 kHz u16), 12 MFCC, %d templates; "
+                               "the CPU arm times a bounded sample per step" % T,
                    "utterances_per_step": S, "samples_per_utterance": U, "templates": T},
         "mfcc_frames_per_s": frames / (ms / 1e3),
         "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": kind, "sample": sample},
@@ -177,12 +216,14 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="utterances per GPU per step")
     ap.add_argument("--templates", type=int, default=20)
-    ap.add_argument("--cpu-sample-per-core", type=int, default=512)
+    ap.add_argument("--cpu-sample-per-core", type=int, default=512, help="cpu_baseline leg of the B200 arm (one shot)")
+    ap.add_argument("--ref-sample-per-core", type=int, default=128, help="--impl reference: utterances per core per step")
+    ap.add_argument("--ref-procs", type=int, default=0, help="CPU worker count (0 = usable cores: affinity capped by cgroup quota)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -205,7 +246,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch, args.templates
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)                 # every kernel, copy, event and collective of the bench runs here
+    torch.cuda.set_stream(stream)
     h = sr_b200.Handle(local)
     h.set_stream(stream.cuda_stream)
 
@@ -237,23 +279,24 @@ def main():
     def step():
         h.recognise_dev(pcm.data_ptr(), U, B, N_LEN, **outs)
         if world > 1:                                   # the one exchange step of the path
-            dist.all_gather_into_tensor(gathered, score)
+            dist.all_gather_into_tensor(gathered, score)   # == sr_b200.dist.gather_blocks for equal blocks
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                # started before warm-up: nvidia-smi needs ~1 s to come up
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches0 = h.launch_count()
-    h.timing_enable(8 * args.steps + 8)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    h.timing_enable(6 * args.steps + 8)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
@@ -292,7 +335,7 @@ def main():
         if rc != 0:
             raise RuntimeError(sr_b200.lib().sr_last_error(he._h))
 
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
         e2e_step()
     barrier()
@@ -336,7 +379,7 @@ def main():
     cpu = None
     parity = None
     if not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = args.ref_procs if args.ref_procs > 0 else usable_cores()
         S = min(B, args.cpu_sample_per_core * cores)
         pcm_s = pcm[:S].cpu().numpy().view(np.uint16)
         bank_h = bank.cpu().numpy()

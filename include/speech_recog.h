@@ -95,7 +95,8 @@ typedef struct sr_handle sr_handle;
 
 int         sr_create(int device, sr_handle **out);       /* device ordinal; <0 = current device     */
 int         sr_destroy(sr_handle *h);
-int         sr_set_stream(sr_handle *h, void *cuda_stream /* cudaStream_t, NULL = handle's own */);
+int         sr_set_stream(sr_handle *h, void *cuda_stream /* cudaStream_t used verbatim; NULL = legacy default stream */);
+int         sr_use_own_stream(sr_handle *h);              /* back to the handle's private non-blocking stream (the default) */
 int         sr_sync(sr_handle *h);
 const char *sr_last_error(const sr_handle *h /* NULL: last error of the calling thread */);
 int         sr_device_count(void);                        /* 0 when no CUDA device is usable         */

@@ -42,6 +42,8 @@ struct sr_handle {
     int num_sms = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                 // H2D of the next chunk while the current one computes
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
     std::string err;
     // template bank
@@ -149,6 +151,12 @@ int sr_create(int device, sr_handle **out) {
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(nullptr, "cudaStreamCreate", e); }
     h->stream = h->own_stream;
+    e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { delete h; return fail(nullptr, "stream/event creation", e); }
     if (!dev_tables()) { cudaStreamDestroy(h->own_stream); delete h; return fail(nullptr, "table upload", cudaErrorInitializationError); }
     *out = h;
     return 0;
@@ -163,13 +171,21 @@ int sr_destroy(sr_handle *h) {
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     delete h;
     return 0;
 }
 
 int sr_set_stream(sr_handle *h, void *cuda_stream) {
     SR_REQUIRE(h, h != nullptr);
-    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);     // used verbatim: NULL is CUDA's legacy default stream
+    return 0;
+}
+
+int sr_use_own_stream(sr_handle *h) {
+    SR_REQUIRE(h, h != nullptr);
+    h->stream = h->own_stream;
     return 0;
 }
 
@@ -421,13 +437,22 @@ int sr_dtw_batch(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, 
     return 0;
 }
 
+// Host-buffer spch_recg for B utterances. Large batches are processed in chunks through two device PCM
+// buffers: the H2D copy of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream), so
+// with pinned host memory the call is bound by max(PCIe, compute) instead of their sum.
 int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, const sr_recog_out *o) {
     SR_REQUIRE(h, h && o && (B == 0 || pcm));
+    SR_REQUIRE(h, U <= 65535u && n_len <= U);
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     const size_t T = h->n_slot;
-    SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));
-    H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
+    // chunk: ~128 MB of PCM, a multiple of 8 utterances (keeps every chunk base 16-byte aligned)
+    uint32_t chunk = (uint32_t)(((size_t)128 << 20) / ((size_t)U * 2));
+    chunk = chunk < 8 ? 8 : (chunk & ~7u);
+    if (chunk > B) chunk = B;
+    const uint32_t nchunks = (B + chunk - 1) / chunk;
+    const size_t chunk_bytes = (((size_t)chunk * U * 2 + 255) / 256) * 256;
+    SR_CK(h, ensure(h->pcm, (nchunks > 1 ? 2 : 1) * chunk_bytes + 16));
     sr_recog_out d;
     memset(&d, 0, sizeof d);
     if (o->atap) { SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag))); d.atap = static_cast<atap_tag *>(h->atap.p);
@@ -439,8 +464,30 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     if (o->best_dis) { SR_CK(h, ensure(h->bdis, (size_t)B * 4)); d.best_dis = static_cast<u32 *>(h->bdis.p); }
     if (o->cmd) { SR_CK(h, ensure(h->cmd, (size_t)B * 4)); d.cmd = static_cast<u32 *>(h->cmd.p); }
     if (o->status) { SR_CK(h, ensure(h->status, (size_t)B)); d.status = static_cast<u8 *>(h->status.p); }
-    int rc = sr_recognise_batch_dev(h, static_cast<const u16 *>(h->pcm.p), U, B, n_len, &d);
-    if (rc) return rc;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t b0 = c * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
+        const int buf = (int)(c & 1);
+        u16 *dpcm = reinterpret_cast<u16 *>(static_cast<unsigned char *>(h->pcm.p) + (size_t)buf * chunk_bytes);
+        cudaStream_t cs = nchunks > 1 ? h->copy_stream : h->stream;
+        if (nchunks > 1 && c >= 2) SR_CK(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));      // buffer free again
+        SR_CK(h, cudaMemcpyAsync(dpcm, pcm + (size_t)b0 * U, (size_t)nb * U * 2, cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1) {
+            SR_CK(h, cudaEventRecord(h->ev_h2d[buf], cs));
+            SR_CK(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[buf], 0));
+        }
+        sr_recog_out dc = d;
+        if (d.atap) dc.atap = d.atap + b0;
+        if (d.seg_off) dc.seg_off = d.seg_off + (size_t)b0 * 6;
+        if (d.ftr) dc.ftr = d.ftr + b0;
+        if (d.score) dc.score = d.score + (size_t)b0 * T;
+        if (d.best_idx) dc.best_idx = d.best_idx + b0;
+        if (d.best_dis) dc.best_dis = d.best_dis + b0;
+        if (d.cmd) dc.cmd = d.cmd + b0;
+        if (d.status) dc.status = d.status + b0;
+        int rc = sr_recognise_batch_dev(h, dpcm, U, nb, n_len, &dc);
+        if (rc) return rc;
+        if (nchunks > 1) SR_CK(h, cudaEventRecord(h->ev_done[buf], h->stream));
+    }
     if (o->atap) D2H(h, o->atap, d.atap, (size_t)B * sizeof(atap_tag));
     if (o->seg_off) D2H(h, o->seg_off, d.seg_off, (size_t)B * 24);
     if (o->ftr)

@@ -18,6 +18,13 @@
 //   exchange through a padded shared buffer (conflict-free both ways);
 //   block B (q3):   4 stage-3 butterflies (groups m4) + 4 stage-4 butterflies (q4=q3+64*m3),
 //                   only output legs 0,1 (bins < 512, MFCC.C:49) are formed.
+//
+// s16 stores without wrap: the asm stores every stage result with STRH (low 16 bits). On THIS path the
+// wrap can never trigger: the stage-0 outputs are real with |.| <= 8192 (an s16 sample >> 2); a radix-4
+// stage maps complex magnitudes <= M to magnitudes <= (M + 3*1.00015*M)/4 + 3 (twiddle rounding
+// |W| <= 1.00015, a few LSB of floor rounding), so after four stages every component is <= 8209 << 32767
+// and the sign-extending truncation is the identity (also no 32-bit overflow: 2*8209*16385 < 2^31).
+// The generic kernel below keeps the wrap because it accepts arbitrary complex input.
 #include "sr_common.cuh"
 
 namespace srk {
@@ -27,7 +34,6 @@ constexpr int kMfccThreads = (kConsumerWarps + 1) * 32;
 constexpr int kNBuf = 3;
 constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
 constexpr int kFftWords = 1024 + 64;         // +4 words per 64
-constexpr int kEWords = 512 + 64;            // +4 words per 32
 
 struct __align__(16) MfccSmem {
     unsigned char pcm[kNBuf][kPcmBufBytes];
@@ -36,7 +42,6 @@ struct __align__(16) MfccSmem {
     u16 tri_even[512];
     u16 tri_odd[512];
     u32 fftbuf[kConsumerWarps][kFftWords];
-    u32 ebuf[kConsumerWarps][kEWords];
     s32 wq[kConsumerWarps][160];
     u32 seq[kConsumerWarps][2][64];
     u32 lg[kConsumerWarps][32];
@@ -46,7 +51,6 @@ struct __align__(16) MfccSmem {
 };
 
 __device__ __forceinline__ int padF(int e) { return e + ((e >> 6) << 2); }
-__device__ __forceinline__ int padE(int k) { return k + ((k >> 5) << 2); }
 
 // (u32)(log((double)v)*100) via the exact threshold table (MFCC.C:168; log(0) pinned to 0)
 __device__ __forceinline__ u32 log100(u32 v, const u32 *thr) {
@@ -152,7 +156,6 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
 
     // ================================ consumer warps ============================================
     u32 *fb = sm.fftbuf[warp];
-    u32 *eb = sm.ebuf[warp];
     s32 *wq = sm.wq[warp];
     const int q1 = lane & 3;
     // stage-1 twiddles (table block N=16, triple q1: legs K2 -> p2, K1 -> p1; leg 3 is all-zero)
@@ -215,7 +218,7 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
                     u32 o[8];
                     cxadda4<14>(a, 0u, Br, Bi, Cr, Ci, 0u, 0u, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
 #pragma unroll
-                    for (int m1 = 0; m1 < 4; ++m1) { vr[m2][m1] = sx16(o[2 * m1]); vi[m2][m1] = sx16(o[2 * m1 + 1]); }
+                    for (int m1 = 0; m1 < 4; ++m1) { vr[m2][m1] = o[2 * m1]; vi[m2][m1] = o[2 * m1 + 1]; }   // STRH wrap is the identity here (|.| <= 8209, see header)
                 }
 #pragma unroll
                 for (int m1 = 0; m1 < 4; ++m1) {
@@ -254,7 +257,7 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
                     u32 o[8];
                     cxadda4<14>(lo16s(p[0]), hi16s(p[0]), Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
 #pragma unroll
-                    for (int m3 = 0; m3 < 4; ++m3) { vr[m4][m3] = sx16(o[2 * m3]); vi[m4][m3] = sx16(o[2 * m3 + 1]); }
+                    for (int m3 = 0; m3 < 4; ++m3) { vr[m4][m3] = o[2 * m3]; vi[m4][m3] = o[2 * m3 + 1]; }
                 }
 #pragma unroll
                 for (int m3 = 0; m3 < 4; ++m3) {
@@ -268,10 +271,11 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
                     u32 o[8];
                     cxadda4<14>(vr[0][m3], vi[0][m3], Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
                     // bins q4 (leg 0) and q4+256 (leg 1); legs 2,3 are bins >= 512, unused (MFCC.C:49)
-                    const u32 m0 = mag10(sx16(o[0]), sx16(o[1]));
-                    const u32 m1 = mag10(sx16(o[2]), sx16(o[3]));
-                    eb[padE(q4)] = m0 * m0;                                 // MFCC.C:131 (u32 wrap)
-                    eb[padE(q4 + 256)] = m1 * m1;
+                    const u32 m0 = mag10_small(o[0], o[1]);
+                    const u32 m1 = mag10_small(o[2], o[3]);
+                    // energies overwrite FFT slots this lane has already consumed (e mod 64 == q3): no hazard
+                    fb[padF(q4)] = m0 * m0;                                 // MFCC.C:131 (u32 wrap)
+                    fb[padF(q4 + 256)] = m1 * m1;
                 }
             }
             __syncwarp();
@@ -279,7 +283,7 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
             // ---- triangular filters, MFCC.C:136-162: lane owns bins [16*lane, 16*lane+16) ------
             {
                 u32 E[16];
-                const uint4 *e4 = reinterpret_cast<const uint4 *>(eb + 16 * lane + 4 * (lane >> 1));
+                const uint4 *e4 = reinterpret_cast<const uint4 *>(fb + 16 * lane + 4 * (lane >> 2));   // padF(16*lane)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const uint4 v = e4[j]; E[4 * j] = v.x; E[4 * j + 1] = v.y; E[4 * j + 2] = v.z; E[4 * j + 3] = v.w; }
                 const uint4 *te4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
@@ -287,17 +291,18 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
                 u32 te[8], to[8];
                 { const uint4 a = te4[0], c = te4[1]; te[0] = a.x; te[1] = a.y; te[2] = a.z; te[3] = a.w; te[4] = c.x; te[5] = c.y; te[6] = c.z; te[7] = c.w; }
                 { const uint4 a = to4[0], c = to4[1]; to[0] = a.x; to[1] = a.y; to[2] = a.z; to[3] = a.w; to[4] = c.x; to[5] = c.y; to[6] = c.z; to[7] = c.w; }
-                u32 s0e = 0, s1e = 0, s0o = 0, s1o = 0;
+                u32 s0e = 0, tote = 0, s0o = 0, toto = 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const u32 we = (i & 1) ? (te[i >> 1] >> 16) : (te[i >> 1] & 0xFFFFu);
                     const u32 wo = (i & 1) ? (to[i >> 1] >> 16) : (to[i >> 1] & 0xFFFFu);
                     const u32 ve = (E[i] * we) / 100u, vo = (E[i] * wo) / 100u;
-                    if (i < sp_e) s0e += ve; else s1e += ve;
-                    if (i < sp_o) s0o += vo; else s1o += vo;
+                    tote += ve; toto += vo;
+                    if (i < sp_e) s0e += ve;
+                    if (i < sp_o) s0o += vo;
                 }
-                *reinterpret_cast<uint2 *>(&sm.seq[warp][0][2 * lane]) = make_uint2(s0e, s1e);
-                *reinterpret_cast<uint2 *>(&sm.seq[warp][1][2 * lane]) = make_uint2(s0o, s1o);
+                *reinterpret_cast<uint2 *>(&sm.seq[warp][0][2 * lane]) = make_uint2(s0e, tote - s0e);
+                *reinterpret_cast<uint2 *>(&sm.seq[warp][1][2 * lane]) = make_uint2(s0o, toto - s0o);
             }
             __syncwarp();
             // ---- filter totals + log, MFCC.C:165-170 -------------------------------------------

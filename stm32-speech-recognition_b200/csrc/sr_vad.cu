@@ -4,14 +4,17 @@
 // async copy (TMA engine) and both functions run on the staged copy, so HBM traffic is the
 // algorithmic 2*U bytes per utterance.
 //   * noise_atap: lane-strided sums / maxima + warp reductions;
-//   * VAD features: one lane per 20 ms frame. frm_sum is order independent; the band-crossing
-//     count depends on `last_sig`, which the reference never resets between frames (VAD.C:99), so a
-//     frame's result depends on the class of the last out-of-band sample at index <= i_k+78.
+//   * VAD features: frames overlap by 50 %, so the scan works on 80-sample BLOCKS (each sample is
+//     touched once) and frame k = block k + block k+1. A block summary is a small monoid element:
+//     sum |x-mid|, number of class alternations among its out-of-band samples, class of the last
+//     out-of-band sample (the first one follows from the parity of the alternations). The band-
+//     crossing count of the reference depends on `last_sig`, which is never reset between frames
+//     (VAD.C:99): entering frame k it is the class of the last out-of-band sample at index <= i_k+78.
 //     Only ONE pair per frame can see that carried-in state (the pair ending at the frame's first
-//     out-of-band sample), so each lane counts crossings with an "unknown" initial state, records
-//     the class/position of its first out-of-band sample and block summaries, and the carried state
-//     is applied afterwards in a short serial pass that also runs the 4-state endpoint FSM
-//     (VAD.C:164-216).
+//     out-of-band sample), so it is applied as a +1 correction; the carry itself is a warp scan.
+//   * endpoint FSM (VAD.C:164-216): 8 consecutive active frames open a segment at the first of
+//     them, 11 consecutive inactive frames close it at the first of those -- evaluated with bit
+//     tricks on the per-frame activity bitmap (one 32-frame word per lane) instead of a serial walk.
 #include "sr_common.cuh"
 
 namespace srk {
@@ -34,15 +37,16 @@ __device__ __forceinline__ u32 warp_max(u32 v) {
     return v;
 }
 
-// per-frame record produced by the parallel pass
-//   bits 0..7 zc0 (crossings with unknown initial state), 8..9 class of first out-of-band sample,
-//   bit 10 that sample is not at position 0, 11..12 last class in [0,78], 13..14 last class in [0,79],
-//   bit 15 frm_sum > s_thl
-__device__ __forceinline__ u32 frame_scan(const VadWarpView &v, u32 i0, u32 mid, u32 a_thl, u32 b_thl, u32 s_thl) {
-    u32 frm_sum = 0, zc = 0, last = 0, first_cls = 0, first_pos1 = 0, la = 0, lf = 0;
+// per-block summary: bs = sum |x-mid| over the 80 samples; flags = zc (bits 0..6, alternations inside the
+// block) | lc << 7 (class of last out-of-band sample, 0 none / 1 below / 2 above) | lcA << 9 (same over the
+// first 79 samples) | p0 << 11 (sample 0 is out of band)
+__device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid, u32 a_thl, u32 b_thl, u32 &bs_out,
+                                           u32 &flags_out) {
+    u32 bs = 0, zc = 0, lcA = 0;
+    bool lastHi = false, lastLo = false, p0 = false;
     const u16 *p = v.x + i0;
-#pragma unroll 1
-    for (int c = 0; c < 20; ++c) {
+#pragma unroll 2
+    for (int c = 0; c < 10; ++c) {
         u32 w[4];
         if (v.vec_ok) {
             const uint4 q = *reinterpret_cast<const uint4 *>(p + 8 * c);
@@ -53,26 +57,38 @@ __device__ __forceinline__ u32 frame_scan(const VadWarpView &v, u32 i0, u32 mid,
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int h = 8 * c + j;
             const u32 s = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu);
-            frm_sum += s > mid ? s - mid : mid - s;                       // VAD.C:126-129
-            const u32 cls = s >= a_thl ? 2u : (s < b_thl ? 1u : 0u);      // VAD.C:134-141 / 143-156
-            // test of sample h against the state left by samples < h (h >= 1), then update from sample h
-            if (h >= 1) {
-                zc += (cls != 0 && last != 0 && cls != last) ? 1u : 0u;
-                if (cls != 0 && first_cls == 0) { first_cls = cls; first_pos1 = 1; }
-            } else if (cls != 0) {
-                first_cls = cls; first_pos1 = 0;
-            }
-            // NOTE: the reference updates from sample h only for h <= 158; sample 159 is tested, never
-            // "updated from" inside this frame -- irrelevant here because nothing is tested after it.
-            if (cls != 0) last = cls;
-            if (h == 78) la = last;
-            if (h == 79) lf = last;
+            bs = __usad(s, mid, bs);                                        // VAD.C:126-129
+            const bool hi = s >= a_thl;                                     // VAD.C:134-141: ">= a" first, else "< b"
+            const bool lo = !hi && s < b_thl;
+            zc += ((hi && lastLo) || (lo && lastHi)) ? 1u : 0u;             // VAD.C:143-156
+            lastHi = hi || (lastHi && !lo);
+            lastLo = lo || (lastLo && !hi);
+            if (c == 0 && j == 0) p0 = hi || lo;
+            if (c == 9 && j == 6) lcA = lastHi ? 2u : (lastLo ? 1u : 0u);   // after sample 78
         }
     }
-    return (zc & 0xFFu) | (first_cls << 8) | (first_pos1 << 10) | (la << 11) | (lf << 13) |
-           ((frm_sum > s_thl ? 1u : 0u) << 15);
+    const u32 lc = lastHi ? 2u : (lastLo ? 1u : 0u);
+    bs_out = bs;
+    flags_out = zc | (lc << 7) | (lcA << 9) | ((p0 ? 1u : 0u) << 11);
+}
+
+// position of the first set bit at index >= from in a bitmap held one 32-bit word per lane; -1 if none
+__device__ __forceinline__ int find_first(u32 word, int lane, int from) {
+    const int fw = from >> 5, fb = from & 31;
+    u32 m = lane > fw ? word : (lane == fw ? (word & (0xFFFFFFFFu << fb)) : 0u);
+    if (from >= 1024) m = 0;
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, m != 0);
+    if (!bal) return -1;
+    const int L = __ffs(bal) - 1;
+    const u32 mw = __shfl_sync(0xFFFFFFFFu, m, L);
+    return 32 * L + __ffs(mw) - 1;
+}
+// bitmap shift towards index 0: result[i] = x[i+s], 0 < s < 32
+__device__ __forceinline__ u32 bm_shr(u32 x, int s, int lane) {
+    u32 nxt = __shfl_down_sync(0xFFFFFFFFu, x, 1);
+    if (lane == 31) nxt = 0;
+    return (x >> s) | (nxt << (32 - s));
 }
 
 __global__ void __launch_bounds__(kVadMaxWarps * 32)
@@ -162,33 +178,66 @@ vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, in
             // the reference (int -> u32 compare) -- here: no frames.
             u32 nfr = buf_len > SR_FRAME_LEN ? (buf_len - SR_FRAME_LEN + SR_FRAME_MOV - 1) / SR_FRAME_MOV : 0;
             if (buf_len > U) nfr = 0;
-            for (u32 k = lane; k < nfr; k += 32) info[k] = frame_scan(v, 80u * k, mid, a_thl, b_thl, at.s_thl);
-            __syncwarp();
             u32 seg[6] = {SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL};
-            u32 carry = 0, cur = 0, front = 0, back = 0, valid_con = 0;
-            for (u32 k = 0; k < nfr; ++k) {
-                const u32 r = info[k];
-                const u32 la = (r >> 11) & 3u, lf = (r >> 13) & 3u, fc = (r >> 8) & 3u;
-                const u32 init = k == 0 ? 0u : (la ? la : carry);              // class of last out-of-band sample <= i+78
-                u32 zc = r & 0xFFu;
-                if (((r >> 10) & 1u) && init != 0 && init != fc) ++zc;
-                if (lf) carry = lf;
-                const bool active = ((r >> 15) & 1u) || zc > at.z_thl;         // VAD.C:164
-                const u32 i = 80u * k;
-                if (active) {
-                    if (cur == 0) { cur = 1; front = 1; }
-                    else if (cur == 1) { if (++front >= 8) { cur = 2; seg[2 * valid_con] = i - 7 * 80; front = 0; } }
-                    else if (cur == 3) { back = 0; cur = 2; }
-                } else {
-                    if (cur == 2) { cur = 3; back = 1; }
-                    else if (cur == 3) {
-                        if (++back >= 11) {
-                            cur = 0;
-                            seg[2 * valid_con + 1] = i - 11 * 80 + 160;
-                            if (++valid_con == SR_MAX_VC_CON) break;
-                            back = 0;
-                        }
-                    } else if (cur == 1) { front = 0; cur = 0; }
+            if (nfr > 0) {
+                const u32 nblk = nfr + 1;                                      // frame k = blocks k, k+1
+                for (u32 blk = lane; blk < nblk; blk += 32) {
+                    u32 bs, fl;
+                    block_scan(v, 80u * blk, mid, a_thl, b_thl, bs, fl);
+                    info[2 * blk] = bs; info[2 * blk + 1] = fl;
+                }
+                __syncwarp();
+                u32 aw = 0;                                                    // lane j: activity of frames 32j..32j+31
+                u32 cin = 0;                                                   // class of last out-of-band sample before this pass
+                for (u32 k0 = 0, j = 0; k0 < nfr; k0 += 32, ++j) {
+                    const u32 k = k0 + lane;
+                    const bool ok = k < nfr;
+                    u32 bs0 = 0, f0 = 0, bs1 = 0, f1 = 0;
+                    if (ok) { bs0 = info[2 * k]; f0 = info[2 * k + 1]; bs1 = info[2 * k + 2]; f1 = info[2 * k + 3]; }
+                    const u32 zc0 = f0 & 127u, lc0 = (f0 >> 7) & 3u, lcA0 = (f0 >> 9) & 3u, p00 = (f0 >> 11) & 1u;
+                    const u32 zc1 = f1 & 127u, lc1 = (f1 >> 7) & 3u;
+                    const u32 fc0 = lc0 ? ((zc0 & 1u) ? 3u - lc0 : lc0) : 0u;      // first class from last class + parity
+                    const u32 fc1 = lc1 ? ((zc1 & 1u) ? 3u - lc1 : lc1) : 0u;
+                    // inclusive "last out-of-band class" scan over the blocks of this pass
+                    u32 inc = lc0;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const u32 up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                        if (lane >= o && inc == 0) inc = up;
+                    }
+                    if (inc == 0) inc = cin;
+                    u32 prev = __shfl_up_sync(0xFFFFFFFFu, inc, 1);               // carry of block k-1
+                    if (lane == 0) prev = cin;
+                    cin = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    const u32 init = k == 0 ? 0u : (lcA0 ? lcA0 : prev);          // class of last out-of-band sample <= i+78
+                    u32 zc = zc0 + zc1 + ((lc0 && fc1 && lc0 != fc1) ? 1u : 0u);
+                    const u32 F = fc0 ? fc0 : fc1;
+                    const bool pos1 = fc0 ? (p00 == 0) : (fc1 != 0);              // first out-of-band sample not at position 0
+                    if (pos1 && init != 0 && init != F) ++zc;
+                    const bool active = ok && ((bs0 + bs1) > at.s_thl || zc > at.z_thl);   // VAD.C:164
+                    const u32 word = __ballot_sync(0xFFFFFFFFu, active);
+                    if ((u32)lane == j) aw = word;
+                }
+                // ---- endpoint FSM on the bitmap ------------------------------------------------------
+                const u32 fullw = nfr >> 5, rem = nfr & 31u;
+                const u32 vmask = (u32)lane < fullw ? 0xFFFFFFFFu : ((u32)lane == fullw ? ((1u << rem) - 1u) : 0u);
+                u32 a8 = aw & bm_shr(aw, 1, lane);
+                a8 &= bm_shr(a8, 2, lane);
+                a8 &= bm_shr(a8, 4, lane);                                     // a8[i]: frames i..i+7 all active
+                u32 z = ~aw & vmask;
+                u32 z8 = z & bm_shr(z, 1, lane);
+                z8 &= bm_shr(z8, 2, lane);
+                z8 &= bm_shr(z8, 4, lane);
+                const u32 z11 = z8 & bm_shr(z8, 3, lane);                      // z11[i]: frames i..i+10 all inactive
+                int cur = 0;
+                for (int sgi = 0; sgi < (int)SR_MAX_VC_CON; ++sgi) {
+                    const int pfr = find_first(a8, lane, cur);
+                    if (pfr < 0) break;
+                    seg[2 * sgi] = 80u * (u32)pfr;                             // VAD.C:178: i - 7*80 with i = 80*(pfr+7)
+                    const int q = find_first(z11, lane, pfr + 8);
+                    if (q < 0) break;                                          // never closes: end stays NULL
+                    seg[2 * sgi + 1] = 80u * (u32)q + 80u;                     // VAD.C:201: i - 11*80 + 160 with i = 80*(q+10)
+                    cur = q + 11;
                 }
             }
             if (lane < 6) {
@@ -210,7 +259,7 @@ cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int
     if (do_vad && buf_len > need) need = buf_len;
     if (need > U) need = U;
     const u32 buf_bytes = ((need * 2 + 32 + 127) / 128) * 128;
-    const u32 max_frames = (buf_len > 160 ? (buf_len - 160 + 79) / 80 : 0) + 1;
+    const u32 max_frames = 2 * ((buf_len > 160 ? (buf_len - 160 + 79) / 80 : 0) + 2);   // 2 words per 80-sample block
     const size_t per_warp = (size_t)buf_bytes + (size_t)max_frames * 4;
     int warps = (int)((220 * 1024) / per_warp);
     if (warps < 1) return cudaErrorInvalidValue;

@@ -48,6 +48,7 @@ def lib():
         L.sr_create.argtypes = [i32, C.POINTER(vp)]
         L.sr_destroy.argtypes = [vp]
         L.sr_set_stream.argtypes = [vp, vp]
+        L.sr_use_own_stream.argtypes = [vp]
         L.sr_sync.argtypes = [vp]
         L.sr_last_error.argtypes = [vp]
         L.sr_last_error.restype = C.c_char_p
