@@ -166,6 +166,10 @@ int sr_get_dis_batch(sr_handle *h, const int16_t *a, const int16_t *b, uint32_t 
  * on arbitrary complex data */
 int sr_fft_raw_batch(sr_handle *h, const uint32_t *in_packed, uint32_t n, uint32_t *out_packed);
 
+/* test hook: count of float bit patterns in [lo_bits, hi_bits) where the kernels' branch-free sqrt differs
+ * from the IEEE sqrt.rn.f32 (0 over [1.0f, 2^33), the range the path can produce) */
+int sr_debug_sqrt_mismatches(sr_handle *h, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches);
+
 /* Per-kernel device timing: after sr_timing_enable(h, max_records) every kernel launch of this handle is
  * bracketed by a CUDA event pair on the launching stream; sr_timing_collect synchronises the stream and
  * returns (tag, milliseconds) per launch in issue order, then rearms. Tags: 0 noise_atap+VAD, 1 get_mfcc,

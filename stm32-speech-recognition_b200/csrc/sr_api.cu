@@ -26,6 +26,7 @@ cudaError_t launch_best_final(const u64 *best, u32 B, u32 *best_idx, u32 *best_d
                               cudaStream_t st);
 cudaError_t launch_status(const u32 *seg_off, const void *ftr, u32 B, u8 *status, cudaStream_t st);
 cudaError_t launch_get_dis(const s16 *a, const s16 *b, u32 n, u32 *out, cudaStream_t st);
+cudaError_t launch_sqrt_check(u32 lo, u32 hi, unsigned long long *bad_dev, cudaStream_t st);
 }  // namespace srk
 
 using namespace srk;
@@ -545,6 +546,19 @@ int sr_get_dis_batch(sr_handle *h, const int16_t *a, const int16_t *b, uint32_t 
     SR_CK(h, launch_get_dis(static_cast<const s16 *>(h->misc0.p), static_cast<const s16 *>(h->misc1.p), n, static_cast<u32 *>(h->misc2.p), h->stream));
     ++h->launches;
     D2H(h, dis, h->misc2.p, (size_t)n * 4);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// test hook: number of float bit patterns in [lo_bits, hi_bits) for which the branch-free sqrt differs from
+// the IEEE intrinsic (must be 0 over [1.0f, 2^33) = the range the kernels feed it)
+int sr_debug_sqrt_mismatches(sr_handle *h, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches) {
+    SR_REQUIRE(h, h && mismatches);
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->misc2, 16));
+    SR_CK(h, cudaMemsetAsync(h->misc2.p, 0, 8, h->stream));
+    SR_CK(h, launch_sqrt_check(lo_bits, hi_bits, static_cast<unsigned long long *>(h->misc2.p), h->stream));
+    D2H(h, mismatches, h->misc2.p, 8);
     SR_CK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -187,6 +187,20 @@ __global__ void status_kernel(const u32 *seg_off, const unsigned char *ftr, u32 
     status[i] = st;
 }
 
+// exhaustive self-check of sqrt_rn_normal against the IEEE intrinsic over float bit patterns [lo, hi)
+__global__ void sqrt_check_kernel(u32 lo, u32 hi, unsigned long long *bad) {
+    unsigned long long n = 0;
+    for (u64 b = (u64)lo + blockIdx.x * (u64)blockDim.x + threadIdx.x; b < hi; b += (u64)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((u32)b);
+        if (__float_as_uint(sqrt_rn_normal(x)) != __float_as_uint(__fsqrt_rn(x))) ++n;
+    }
+    if (n) atomicAdd(bad, n);
+}
+cudaError_t launch_sqrt_check(u32 lo, u32 hi, unsigned long long *bad_dev, cudaStream_t st) {
+    sqrt_check_kernel<<<148 * 8, 256, 0, st>>>(lo, hi, bad_dev);
+    return cudaGetLastError();
+}
+
 // get_dis for n independent row pairs (secondary drop-in symbol, DTW.C:45-62)
 __global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -25,16 +25,21 @@
 // |W| <= 1.00015, a few LSB of floor rounding), so after four stages every component is <= 8209 << 32767
 // and the sign-extending truncation is the identity (also no 32-bit overflow: 2*8209*16385 < 2^31).
 // The generic kernel below keeps the wrap because it accepts arbitrary complex input.
+#include <stdio.h>
+#include <stdlib.h>
 #include "sr_common.cuh"
+
+#ifndef SR_MFCC_DEFAULT_WARPS
+#define SR_MFCC_DEFAULT_WARPS 15
+#endif
 
 namespace srk {
 
-constexpr int kConsumerWarps = 16;
-constexpr int kMfccThreads = (kConsumerWarps + 1) * 32;
 constexpr int kNBuf = 3;
 constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
 constexpr int kFftWords = 1024 + 64;         // +4 words per 64
 
+template <int kConsumerWarps>
 struct __align__(16) MfccSmem {
     unsigned char pcm[kNBuf][kPcmBufBytes];
     int2 tw[340 * 3];
@@ -71,11 +76,12 @@ __device__ __forceinline__ int mfcc_frames(u32 start, u32 end, u32 U) {
     return n > SR_VV_FRM_MAX ? 0 : (int)n;
 }
 
-__global__ void __launch_bounds__(kMfccThreads, 1)
-mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg, u32 seg_stride,
-            const atap_tag *__restrict__ atap, unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab) {
+template <int kConsumerWarps>
+__device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
+                                          u32 seg_stride, const atap_tag *__restrict__ atap,
+                                          unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MfccSmem &sm = *reinterpret_cast<MfccSmem *>(smem_raw);
+    MfccSmem<kConsumerWarps> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time: tables to shared memory, barriers ------------------------------------------
@@ -330,6 +336,22 @@ mfcc_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ s
     }
 }
 
+// Variants: consumer warps per CTA x register cap (one persistent CTA per SM). More warps fill issue slots that
+// stay idle when only 4 warps per scheduler are resident; fewer registers cost a few spills.
+#define SR_MFCC_VARIANT(W, NREG)                                                                                  \
+    __global__ void __maxnreg__(NREG) mfcc_kernel_w##W(const u16 *__restrict__ pcm, u32 U, u32 B,               \
+                                                       const u32 *__restrict__ seg, u32 seg_stride,              \
+                                                       const atap_tag *__restrict__ atap,                         \
+                                                       unsigned char *__restrict__ ftr,                           \
+                                                       const DevTables *__restrict__ tab) {                      \
+        mfcc_body<W>(pcm, U, B, seg, seg_stride, atap, ftr, tab);                                                 \
+    }
+// threads per CTA are capped at floor(65536 / regs / 128) * 128, so consumer warps + 1 producer = 16 / 20 / 24 / 28
+SR_MFCC_VARIANT(15, 128)
+SR_MFCC_VARIANT(19, 96)
+SR_MFCC_VARIANT(23, 80)
+SR_MFCC_VARIANT(27, 72)
+
 // ---- generic (unpruned) FFT + magnitude: the reference's global `fft` (MFCC.C:27-62) -----------
 // One warp per frame, all five passes in shared memory exactly as the asm orders them. Not on the
 // hot path; it exists for the secondary drop-in symbol and as an on-device cross-check of the
@@ -383,21 +405,41 @@ fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, cons
 }
 
 // ---- host launchers -----------------------------------------------------------------------------
+template <int W, typename K>
+static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride,
+                                       const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfccSmem<W>));
+    if (e != cudaSuccess) return e;
+    const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
+    kern<<<grid, (W + 1) * 32, sizeof(MfccSmem<W>), st>>>(pcm, U, B, seg, seg_stride, atap,
+                                                         static_cast<unsigned char *>(ftr), tab);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess)
+            fprintf(stderr, "mfcc_kernel_w%d launch failed (%s): regs %d, maxThreads %d, static smem %zu, dyn smem %zu (max %d), threads %d\n",
+                    W, cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, sizeof(MfccSmem<W>),
+                    fa.maxDynamicSharedSizeBytes, (W + 1) * 32);
+    }
+    return e;
+}
+
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
                         void *ftr, int num_sms, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfccSmem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     const DevTables *tab = dev_tables();
     if (!tab) return cudaErrorInitializationError;
-    const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
-    mfcc_kernel<<<grid, kMfccThreads, sizeof(MfccSmem), st>>>(pcm, U, B, seg, seg_stride, atap,
-                                                              static_cast<unsigned char *>(ftr), tab);
-    return cudaGetLastError();
+    static int variant = -1;                               // SR_MFCC_WARPS=15|19|23|27 selects a variant (tuning knob)
+    if (variant < 0) {
+        const char *ev = getenv("SR_MFCC_WARPS");
+        variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
+    }
+    switch (variant) {
+    case 23: return launch_mfcc_variant<23>(mfcc_kernel_w23, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
+    case 27: return launch_mfcc_variant<27>(mfcc_kernel_w27, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
+    default: return launch_mfcc_variant<15>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
+    case 19: return launch_mfcc_variant<19>(mfcc_kernel_w19, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
+    }
 }
 
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,

@@ -59,6 +59,7 @@ def lib():
         L.sr_launch_count.restype = u64
         L.sr_timing_enable.argtypes = [vp, u32]
         L.sr_timing_collect.argtypes = [vp, vp, vp, u32, vp]
+        L.sr_debug_sqrt_mismatches.argtypes = [vp, u32, u32, vp]
         L.sr_set_bank.argtypes = [vp, vp, u32, u32]
         L.sr_set_bank_dev.argtypes = [vp, vp, u32, u32]
         for name in ("sr_noise_atap_batch", "sr_noise_atap_batch_dev"):

@@ -28,6 +28,17 @@ def _cmp_recog(out, ref, keys=("seg_off", "score", "best_idx", "best_dis", "cmd"
     assert ob.ftr_equal(out["ftr"], ref["ftr"])
 
 
+def test_fast_sqrt_exhaustive(handle):
+    """the branch-free correctly-rounded sqrt used by mag (MFCC.C:58) and get_dis (DTW.C:59) equals the IEEE
+    intrinsic for EVERY float in [1, 2^33) -- a superset of what (float)(s32 pw) and (float)(u32 d) can be"""
+    import struct
+    lo = struct.unpack("<I", struct.pack("<f", 1.0))[0]
+    hi = struct.unpack("<I", struct.pack("<f", 2.0 ** 33))[0]
+    bad = C.c_uint64(123)
+    rc = sr_b200.lib().sr_debug_sqrt_mismatches(handle._h, lo, hi, C.byref(bad))
+    assert rc == 0 and bad.value == 0
+
+
 # ---- FFT: the asm restatement on device, arbitrary complex inputs -----------------------------------
 def test_fft_raw_bit_exact(handle, ora):
     rng = np.random.default_rng(21)
