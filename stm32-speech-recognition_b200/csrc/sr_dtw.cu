@@ -2,12 +2,15 @@
 // the slope-2 / slope-1/2 parallelogram (dtw_limit, DTW.C:76-109) with the 12-dim integer local
 // distance get_dis (DTW.C:45-62), plus the spch_recg argmin (Src/APP/main.c:276-291) as an epilogue.
 //
-// Mapping: one thread per (utterance, template) pair -- the walk is inherently sequential and
-// data dependent; parallelism is across the B x T pairs. A CTA keeps a tile of 32 templates in
-// shared memory (loaded once, reused for every utterance the CTA visits) and each of its 16 warps
-// walks one utterance against those 32 templates (lane = template), the utterance's rows staged
-// in shared memory too. Local distances use  sum (a-b)^2 = |a|^2 + |b|^2 - 2 a.b  (exact in the
-// ring Z/2^32 in which the reference accumulates), with |row|^2 precomputed per staged row.
+// Mapping: one thread per (utterance, template) pair -- the walk is inherently sequential and data
+// dependent; parallelism is across the B x T pairs. A CTA keeps a tile of up to 32 templates in shared
+// memory (loaded once, reused for every utterance the CTA visits). Its 16 warps are split into groups
+// of Wg warps; a group stages NU utterances at a time and its 32*Wg lanes walk the NU x Tt pairs
+// (flattened), so lanes stay busy when Tt < 32 (the host picks NU/Wg for the tile width).
+// Rows are staged as BYTE PLANES (low bytes | high bytes of the 12 s16), so that
+//   sum (a-b)^2 = |a|^2 + |b|^2 - 2 a.b        (exact in Z/2^32, the ring the reference accumulates in)
+// costs 12 IDP.4A per local distance on packed registers: a.b = 65536*HH + 256*(HL+LH) + LL.
+// dtw_limit is evaluated as a per-column y interval (ya, yb) updated only when x moves.
 #include "sr_common.cuh"
 
 namespace srk {
@@ -67,97 +70,158 @@ __device__ __forceinline__ void row_norms(const unsigned char *rows, u32 *norm, 
     }
 }
 
+// ---- byte-plane rows: 6 words = lo bytes of dims 0..11 (3 words) then hi bytes (3 words) -----------------
+constexpr int kSlotBytes = 119 * 24 + 120 * 4;            // rows + squared norms = 3336
+struct PRow { u32 lo[3], hi[3]; u32 n; };
+
+__device__ __forceinline__ void load_prow(PRow &r, const unsigned char *slot, int idx) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(slot + idx * 24);
+    const uint2 a = p[0], b = p[1], c = p[2];
+    r.lo[0] = a.x; r.lo[1] = a.y; r.lo[2] = b.x; r.hi[0] = b.y; r.hi[1] = c.x; r.hi[2] = c.y;
+    r.n = reinterpret_cast<const u32 *>(slot + 119 * 24)[idx];
+}
+__device__ __forceinline__ u32 dp4a_uu(u32 a, u32 b, u32 c) { u32 d; asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ u32 dp4a_ss(u32 a, u32 b, u32 c) { u32 d; asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ u32 dp4a_su(u32 a, u32 b, u32 c) { u32 d; asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ u32 dp4a_us(u32 a, u32 b, u32 c) { u32 d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// get_dis, DTW.C:45-62
+__device__ __forceinline__ u32 pdist(const PRow &a, const PRow &b) {
+    u32 ll = 0, hh = 0, mx = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ll = dp4a_uu(a.lo[j], b.lo[j], ll);
+        hh = dp4a_ss(a.hi[j], b.hi[j], hh);
+        mx = dp4a_su(a.hi[j], b.lo[j], mx);
+        mx = dp4a_us(a.lo[j], b.hi[j], mx);
+    }
+    const u32 dot = hh * 65536u + mx * 256u + ll;
+    return usqrt_trunc(a.n + b.n - 2u * dot);
+}
+// convert one v_ftr_tag's rows [0,nrows) into the byte-plane slot; threads tid, tid+nthr, ... of the caller
+__device__ __forceinline__ void stage_planes(unsigned char *slot, const unsigned char *src_ftr, int nrows, int tid, int nthr) {
+    for (int r = tid; r < nrows; r += nthr) {
+        const u32 *s = reinterpret_cast<const u32 *>(src_ftr + 4 + r * 24);
+        u32 w[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w[j] = s[j];
+        u32 lo[3], hi[3], nrm = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                      // words 2j, 2j+1 hold dims 4j..4j+3
+            lo[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x6420);
+            hi[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x7531);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const u32 a = lo16s(w[j]), b = hi16s(w[j]);
+            nrm += a * a + b * b;
+        }
+        u32 *d = reinterpret_cast<u32 *>(slot + r * 24);
+        d[0] = lo[0]; d[1] = lo[1]; d[2] = lo[2]; d[3] = hi[0]; d[4] = hi[1]; d[5] = hi[2];
+        reinterpret_cast<u32 *>(slot + 119 * 24)[r] = nrm;
+    }
+}
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+    if (nthreads == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(kDtwWarps * 32)
 dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
            u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best,
-           const u8 *__restrict__ status /* may be NULL: per-utterance SR_ST_* gate of sr_recognise */) {
+           const u8 *__restrict__ status /* may be NULL: per-utterance SR_ST_* gate of sr_recognise */,
+           int Wg, int NU, int G, u32 tile0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    DtwSmem &sm = *reinterpret_cast<DtwSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 t0 = blockIdx.x * kTileT;
+    const u32 t0 = (blockIdx.x + tile0) * kTileT;
+    const int Tt = (int)min((u32)kTileT, T - t0);
+    unsigned char *tile = smem_raw;                                   // Tt slots
+    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)kTileT * kSlotBytes);   // [32]
+    unsigned char *uslots = smem_raw + (size_t)kTileT * kSlotBytes + 128;          // G*NU slots
+    u32 *ufrm = reinterpret_cast<u32 *>(uslots + (size_t)G * NU * kSlotBytes);     // [G*NU]
 
-    // ---- template tile: rows + norms + frame counts ---------------------------------------------
-    for (int tt = warp; tt < kTileT; tt += kDtwWarps) {
-        const u32 t = t0 + tt;
-        u32 frm = 0xFFFFFFFFu;
-        if (t < T) {
-            const unsigned char *slot = bank + (size_t)t * slot_stride;
-            const u32 hdr = *reinterpret_cast<const u32 *>(slot);
-            const u32 sign = hdr & 0xFFFFu;
-            frm = hdr >> 16;
-            if ((flags & SR_DTW_CHECK_SIGN) && sign != SR_SAVE_MASK) frm = 0xFFFFFFFFu;   // main.c:283
-            const int nrows = (frm == 0xFFFFFFFFu) ? 0 : (int)min(frm + 1u, 119u);        // +1: the do-while may touch row frm
-            stage_rows(sm.trow[tt], sm.tnorm[tt], slot, nrows, lane, 32);
-            __syncwarp();
-            row_norms(sm.trow[tt], sm.tnorm[tt], nrows, lane, 32);
-        }
-        if (lane == 0) sm.tfrm[tt] = frm;
+    // ---- template tile: byte-plane rows + norms + frame counts ----------------------------------------
+    for (int tt = warp; tt < Tt; tt += kDtwWarps) {
+        const unsigned char *slot = bank + (size_t)(t0 + tt) * slot_stride;
+        const u32 hdr = *reinterpret_cast<const u32 *>(slot);
+        u32 frm = hdr >> 16;
+        if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;   // main.c:283
+        if (frm > 119u && frm != 0xFFFFFFFFu) frm = 0xFFFFFFFEu;                                    // garbage header: no walk
+        const int nrows = (frm >= 0xFFFFFFFEu) ? 0 : (int)min(frm + 1u, 119u);   // +1: the do-while may touch row frm
+        stage_planes(tile + (size_t)tt * kSlotBytes, slot, nrows, lane, 32);
+        if (lane == 0) tfrm[tt] = frm;
     }
     __syncthreads();
 
-    const u32 t = t0 + lane;
-    const u32 Mraw = sm.tfrm[lane];
-    const unsigned char *trow = sm.trow[lane];
-    const u32 *tnorm = sm.tnorm[lane];
-    unsigned char *urow = sm.urow[warp];
-    u32 *unorm = sm.unorm[warp];
+    const int group = warp / Wg, wig = warp - group * Wg;
+    if (group >= G) return;                                            // idle warps (16 not divisible by Wg)
+    const int gthreads = Wg * 32, gtid = wig * 32 + lane;
+    const int ul = gtid / Tt, tl = gtid - ul * Tt;                     // this lane's (utterance slot, template) -- fixed
+    const bool lane_has_pair = ul < NU;
+    unsigned char *gslots = uslots + (size_t)group * NU * kSlotBytes;
+    u32 *gfrm = ufrm + group * NU;
+    const unsigned char *trow = tile + (size_t)tl * kSlotBytes;
+    const u32 Mraw = lane_has_pair ? tfrm[tl] : 0xFFFFFFFFu;
+    const u32 t = t0 + (u32)tl;
 
-    for (u32 u = blockIdx.y * kDtwWarps + warp; u < B; u += gridDim.y * kDtwWarps) {
-        const unsigned char *uf = in_ftr + (size_t)u * kFtrBytes;
-        const u32 Iraw = (*reinterpret_cast<const u32 *>(uf)) >> 16;
-        const bool gated = status && status[u] != SR_ST_OK;          // VAD/MFCC failed: spch_recg returns before dtw
-        __syncwarp();
-        if (!gated) {
-            const int nrows = (int)min(Iraw + 1u, 119u);
-            stage_rows(urow, unorm, uf, nrows, lane, 32);
-            __syncwarp();
-            row_norms(urow, unorm, nrows, lane, 32);
-        }
-        __syncwarp();
-
-        u32 result = SR_DIS_ERR;
-        const int I = (int)Iraw, M = (int)Mraw;
-        bool walk = !gated && t < T && Mraw != 0xFFFFFFFFu && !(I > M * 2 || 2 * I < M) && I <= 119 && M <= 119;   // DTW.C:133
-        if (walk) {
-            const int X1 = (2 * M - I) / 3, X2 = (4 * I - 2 * M) / 3;            // DTW.C:141-142
-            Row i0, i1, m0, m1;
-            load_row(i0, urow, 0); load_row(m0, trow, 0);
-            load_row(i1, urow, 1); load_row(m1, trow, 1);
-            u32 ni0 = unorm[0], ni1 = unorm[1], nm0 = tnorm[0], nm1 = tnorm[1];
-            u32 dis = dist(i0, ni0, m0, nm0);                                      // DTW.C:146
-            int x = 1, y = 1;
-            u32 step = 1;
-            do {                                                                   // DTW.C:150-188
-                const u32 up = inside(x, y + 1, X1, X2, I, M) ? dist(m1, nm1, i0, ni0) : SR_DIS_ERR;
-                const u32 right = inside(x + 1, y, X1, X2, I, M) ? dist(m0, nm0, i1, ni1) : SR_DIS_ERR;
-                const u32 ru = inside(x + 1, y + 1, X1, X2, I, M) ? dist(m1, nm1, i1, ni1) : SR_DIS_ERR;
-                u32 mn = ru;
-                if (mn > right) mn = right;
-                if (mn > up) mn = up;
-                dis += mn;
-                const bool mv_x = (mn == ru) || (mn != up);                         // diag, else up, else right
-                const bool mv_y = (mn == ru) || (mn == up);
-                if (mv_x) { i0 = i1; ni0 = ni1; ++x; }
-                if (mv_y) { m0 = m1; nm0 = nm1; ++y; }
-                ++step;
-                const bool more = (x < I) && (y < M);
-                if (more) {
-                    if (mv_x) { load_row(i1, urow, x); ni1 = unorm[x]; }
-                    if (mv_y) { load_row(m1, trow, y); nm1 = tnorm[y]; }
-                } else break;
-            } while (true);
-            result = dis / (step & 0xFFFFu);                                       // DTW.C:191 (step is u16)
-        }
-        if (t < T && score) score[(size_t)u * T + t] = result;
-        if (best) {                                                                // uniform branch: all 32 lanes shuffle
-            u64 key = t < T ? (((u64)result << 32) | (u64)t) : ~0ull;              // strict '<', first wins == lexicographic min
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const u64 other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
-                key = other < key ? other : key;
+    for (u32 ubase = (blockIdx.y * G + group) * NU; ubase < B; ubase += gridDim.y * G * NU) {
+        // ---- stage NU utterances of this group ---------------------------------------------------------
+        for (int s = 0; s < NU; ++s) {
+            const u32 u = ubase + s;
+            u32 frm = 0xFFFFFFFFu;
+            if (u < B && !(status && status[u] != SR_ST_OK)) {        // VAD/MFCC failed: spch_recg returns before dtw
+                const unsigned char *uf = in_ftr + (size_t)u * kFtrBytes;
+                frm = (*reinterpret_cast<const u32 *>(uf)) >> 16;
+                if (frm > 119u) frm = 0xFFFFFFFEu;
+                else stage_planes(gslots + (size_t)s * kSlotBytes, uf, (int)min(frm + 1u, 119u), gtid, gthreads);
             }
-            if (lane == 0) atomicMin(reinterpret_cast<unsigned long long *>(&best[u]), (unsigned long long)key);
+            if (gtid == 0) gfrm[s] = frm;
         }
+        group_barrier(1 + group, gthreads);
+
+        const u32 u = ubase + (u32)ul;
+        if (lane_has_pair && u < B) {
+            const u32 Iraw = gfrm[ul];
+            u32 result = SR_DIS_ERR;
+            const int I = (int)Iraw, M = (int)Mraw;
+            if (Iraw < 0xFFFFFFFEu && Mraw < 0xFFFFFFFEu && !(I > M * 2 || 2 * I < M)) {             // DTW.C:133
+                const unsigned char *urow = gslots + (size_t)ul * kSlotBytes;
+                const int X1 = (2 * M - I) / 3, X2 = (4 * I - 2 * M) / 3;                             // DTW.C:141-142
+                // dtw_limit (DTW.C:76-109) as an open y interval per column: ins(x,y) <=> yb(x) < y < ya(x)
+                const int ca = 4 - I + 2 * M + 1, cb = M - 2 * I - 4;
+                auto ya = [&](int x) { return x < X1 ? 2 * x + 2 : (x + ca) >> 1; };
+                auto yb = [&](int x) { return x < X2 ? (x - 2) >> 1 : 2 * x + cb; };
+                PRow i0, i1, m0, m1;
+                load_prow(i0, urow, 0); load_prow(m0, trow, 0);
+                load_prow(i1, urow, 1); load_prow(m1, trow, 1);
+                u32 dis = pdist(i0, m0);                                                             // DTW.C:146
+                int x = 1, y = 1;
+                int ya0 = ya(1), yb0 = yb(1), ya1 = ya(2), yb1 = yb(2);
+                u32 step = 1;
+                while (true) {                                                                       // DTW.C:150-188
+                    const u32 d_up = pdist(m1, i0), d_right = pdist(m0, i1), d_ru = pdist(m1, i1);
+                    const u32 up = (y + 1 < ya0 && y + 1 > yb0) ? d_up : SR_DIS_ERR;
+                    const u32 right = (y < ya1 && y > yb1) ? d_right : SR_DIS_ERR;
+                    const u32 ru = (y + 1 < ya1 && y + 1 > yb1) ? d_ru : SR_DIS_ERR;
+                    u32 mn = ru;
+                    if (mn > right) mn = right;
+                    if (mn > up) mn = up;
+                    dis += mn;
+                    const bool mv_x = (mn == ru) || (mn != up);                                       // diag, else up, else right
+                    const bool mv_y = (mn == ru) || (mn == up);
+                    ++step;
+                    if (mv_x) { i0 = i1; ++x; ya0 = ya1; yb0 = yb1; ya1 = ya(x + 1); yb1 = yb(x + 1); }
+                    if (mv_y) { m0 = m1; ++y; }
+                    if (!(x < I && y < M)) break;
+                    if (mv_x) load_prow(i1, urow, x);
+                    if (mv_y) load_prow(m1, trow, y);
+                }
+                result = dis / (step & 0xFFFFu);                                                     // DTW.C:191 (step is u16)
+            }
+            if (score) score[(size_t)u * T + t] = result;
+            if (best) atomicMin(reinterpret_cast<unsigned long long *>(&best[u]),
+                                (unsigned long long)(((u64)result << 32) | (u64)t));   // strict '<', first wins == lexicographic min
+        }
+        group_barrier(1 + group, gthreads);                                                          // before restaging
     }
 }
 
@@ -213,22 +277,49 @@ __global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
     out[i] = usqrt_trunc(d);
 }
 
-cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
-                       u64 *best, const u8 *status, int num_sms, cudaStream_t st) {
-    if (B == 0 || T == 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DtwSmem));
+// one launch for `ntiles` template tiles of width Tt starting at tile `tile0`
+static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags,
+                                    u32 *score, u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 tile0,
+                                    u32 ntiles, int Tt) {
+    // lane packing: groups of Wg warps walk NU utterances x Tt templates; pick the best (Wg, NU, G)
+    const size_t budget = 224 * 1024 - (size_t)kTileT * kSlotBytes - 128 - 256;
+    const int slots_max = (int)(budget / kSlotBytes);
+    int bestWg = 1, bestNU = 1, bestG = kDtwWarps;
+    double best_util = -1.0;
+    for (int Wg = 1; Wg <= 8; ++Wg) {                       // named barriers 1..8
+        const int NU = (32 * Wg) / Tt;
+        if (NU < 1) continue;
+        int G = kDtwWarps / Wg;
+        if (G > slots_max / NU) G = slots_max / NU;
+        if (G < 1) continue;
+        const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kDtwWarps);
+        if (util > best_util + 1e-9) { best_util = util; bestWg = Wg; bestNU = NU; bestG = G; }
+    }
+    const size_t smem = (size_t)kTileT * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
+    cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
-    const u32 tiles = (T + kTileT - 1) / kTileT;
-    u32 gy = ((u32)num_sms + tiles - 1) / tiles;         // 160 KB of shared memory: one CTA per SM
-    const u32 ugroups = (B + kDtwWarps - 1) / kDtwWarps;
+    u32 gy = ((u32)num_sms + ntiles - 1) / ntiles;
+    const u32 ugroups = (B + (u32)(bestG * bestNU) - 1) / (u32)(bestG * bestNU);
     if (gy > ugroups) gy = ugroups;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
-    dim3 grid(tiles, gy);
-    dtw_kernel<<<grid, kDtwWarps * 32, sizeof(DtwSmem), st>>>(static_cast<const unsigned char *>(in_ftr), B,
-                                                             static_cast<const unsigned char *>(bank), T, slot_stride,
-                                                             flags, score, best, status);
+    dim3 grid(ntiles, gy);
+    dtw_kernel<<<grid, kDtwWarps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
+                                                  static_cast<const unsigned char *>(bank), T, slot_stride, flags,
+                                                  score, best, status, bestWg, bestNU, bestG, tile0);
     return cudaGetLastError();
+}
+
+cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st) {
+    if (B == 0 || T == 0) return cudaSuccess;
+    const u32 full = T / kTileT, rem = T % kTileT;
+    if (full) {
+        cudaError_t e = launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, kTileT);
+        if (e != cudaSuccess) return e;
+    }
+    if (rem) return launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, (int)rem);
+    return cudaSuccess;
 }
 cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
