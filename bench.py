@@ -213,6 +213,143 @@ def run_reference(args, rank):
     }))
 
 
+def run_kernel_workload(args):
+    """--workload mfcc | dtw | dtw_band: the single-kernel configurations of BASELINE.json (configs[1] "MFCC kernel
+    roofline" with the fixed segment of SURVEY 8d, configs[2] DTW 65 536 x 200). One GPU, one JSON line each.
+    These are secondary lines for the BASELINE.md table; the driver's contract line is the default workload."""
+    import torch
+    import sr_b200
+    import oracle_bind as ob
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    h = sr_b200.Handle(0)
+    h.set_stream(stream.cuda_stream)
+    B = args.batch
+    cores = args.ref_procs if args.ref_procs > 0 else usable_cores()
+    peak, peak_src = peaks()
+    if args.workload == "stream":
+        # BASELINE configs[4]: 8192 concurrent 5 s streams fed in lock-step chunks; latency = host time from
+        # delivery of the chunk that completes the closing frame (sample end+879) to the result being visible
+        S, L, T = args.streams, 40000, args.templates
+        pin = torch.empty((S, L), dtype=torch.int16).pin_memory()
+        gen = torch.empty((S, L), dtype=torch.int16, device=dev)
+        sr_b200.synth_pcm_dev(gen.data_ptr(), S, L, 0x5EED5000, 3, stream.cuda_stream)
+        pin.copy_(gen)
+        tpl = torch.empty((T, U), dtype=torch.int16, device=dev)
+        sr_b200.synth_pcm_dev(tpl.data_ptr(), T, U, TPL_SEED, 1, stream.cuda_stream)
+        tftr = torch.zeros((T, 2860), dtype=torch.uint8, device=dev)
+        h.set_bank_dev(0, 0, 4096)
+        h.recognise_dev(tpl.data_ptr(), U, T, N_LEN, ftr=tftr.data_ptr())
+        bank = torch.full((T, 4096), 255, dtype=torch.uint8, device=dev)
+        bank[:, :2860] = tftr
+        bank[:, 0], bank[:, 1] = 12345 & 0xFF, 12345 >> 8
+        h.set_bank_dev(bank.data_ptr(), T, 4096)
+        torch.cuda.synchronize(dev)
+        del gen
+        h.use_own_stream()
+        pool = sr_b200.StreamPool(h, S, L, N_LEN)
+        out = {}
+        for chunk in (800, 80):
+            lat, n_events, t_all = [], 0, 0.0
+            for rep in range(2):                                   # rep 0 = warm-up
+                pool.reset()
+                lat, n_events = [], 0
+                t_start = time.perf_counter()
+                for n0 in range(0, L, chunk):
+                    t0 = time.perf_counter()
+                    evs = pool.push(pin.data_ptr() + 2 * n0, chunk, L)
+                    dt = time.perf_counter() - t0
+                    if evs:
+                        lat += [dt] * len(evs)
+                        n_events += len(evs)
+                t_all = time.perf_counter() - t_start
+            lat = np.array(lat) * 1e3
+            out["chunk_%d" % chunk] = {"chunk_ms": chunk / 8.0, "pushes": L // chunk, "events": n_events,
+                                       "latency_ms_p50": float(np.percentile(lat, 50)), "latency_ms_p99": float(np.percentile(lat, 99)),
+                                       "latency_ms_max": float(lat.max()), "wall_s": t_all,
+                                       "realtime_factor": (S * L / 8000.0) / t_all, "utterances_per_s": n_events / t_all}
+        seg, _ = pool.segments()
+        pool.close()
+        ref = h.vad(pin.numpy().view(np.uint16)[:256].copy(), h.noise_atap(pin.numpy().view(np.uint16)[:256].copy(), N_LEN))
+        print(json.dumps({"metric": "p50 per-utterance latency (streaming)", "value": out["chunk_800"]["latency_ms_p50"], "unit": "ms",
+                          "n_gpus": 1, "higher_is_better": False, "data": "synthetic",
+                          "config": {"workload": "configs[4] on 1 GPU: %d concurrent 5 s streams (3 words each), %d templates, lock-step chunks" % (S, T)},
+                          "results": out, "segments_equal_batch_vad_sample": bool(np.array_equal(seg[:256], ref)),
+                          "gpu_launches": h.launch_count()}))
+        return
+    if args.workload == "mfcc":
+        pcm = torch.empty((B, U), dtype=torch.int16, device=dev)
+        sr_b200.synth_pcm_dev(pcm.data_ptr(), B, U, SEED, 1, stream.cuda_stream)
+        seg = torch.tensor([80, 8000], dtype=torch.int32, device=dev).repeat(B, 1).contiguous()
+        atap_h = np.zeros(B, sr_b200.ATAP_DTYPE)
+        atap_h["mid_val"] = 2048
+        atap = torch.from_numpy(atap_h.view(np.uint8).reshape(B, 12)).to(dev)
+        ftr = torch.zeros((B, 2860), dtype=torch.uint8, device=dev)
+        run = lambda: h.mfcc_dev(pcm.data_ptr(), U, B, seg.data_ptr(), 2, atap.data_ptr(), ftr.data_ptr())
+        units, unit_name = B * 98.0, "MFCC frames/s"
+        bytes_per_launch = B * (2.0 * 7921 + 24 * 98 + 4)
+        S = min(B, 64 * cores)
+        o = ob.best_oracle()
+        pcm_s = pcm[:S].cpu().numpy().view(np.uint16)
+        seg_s = np.tile(np.array([80, 8000], np.uint32), (S, 1))
+        t0 = time.perf_counter()
+        ref = o.mfcc_batch(pcm_s, seg_s, atap_h[:S], nthreads=cores) if o.name == "oracle-port" else o.mfcc_batch(pcm_s, seg_s, atap_h[:S])
+        cpu_s = time.perf_counter() - t0
+        cpu = {"value": S * 98 / cpu_s, "unit": unit_name, "cores": cores if o.name == "oracle-port" else 1, "kind": "port" if o.name == "oracle-port" else "reference",
+               "sample": "first %d utterances (fixed segment), single call" % S}
+        check = lambda: ob.ftr_equal(ftr[:S].cpu().numpy().view(sr_b200.FTR_DTYPE).reshape(-1), ref)
+        cfg = "configs[1] kernel view: 65536 x 1 s, fixed segment [80,8000) -> 98 frames/utt, mid 2048 (SURVEY 8d config 2)"
+    else:
+        T = args.templates if args.templates != 20 else 200
+        fin = torch.from_numpy(sr_b200.synth_ftr_host(B, 0xD7A00000, 50, 100)).to(dev)
+        bank_h = sr_b200.synth_ftr_host(T, 0xD7A10000, 50, 100, stride=4096)
+        bank = torch.from_numpy(bank_h).to(dev)
+        h.set_bank_dev(bank.data_ptr(), T, 4096)
+        score = torch.zeros((B, T), dtype=torch.int32, device=dev)
+        bidx = torch.zeros(B, dtype=torch.int32, device=dev)
+        bdis = torch.zeros(B, dtype=torch.int32, device=dev)
+        band = args.workload == "dtw_band"
+        flags = sr_b200.DTW_BAND if band else 0
+        run = lambda: h.dtw_dev(fin.data_ptr(), B, flags, 10, score.data_ptr(), bidx.data_ptr(), bdis.data_ptr())
+        S = min(B, 4 * cores)
+        o = ob.port()
+        fin_s = fin[:S].cpu().numpy().view(sr_b200.FTR_DTYPE).reshape(-1)
+        t0 = time.perf_counter()
+        ref, cells = o.dtw_batch(fin_s, bank_h, T, 4096, band_r=10 if band else -1, nthreads=cores)
+        cpu_s = time.perf_counter() - t0
+        cells_per_pair = cells / float(S * T)
+        units, unit_name = B * T * cells_per_pair, "DTW cells/s (%s)" % ("lattice points in the r=10 band" if band else "get_dis evaluations of the greedy walk")
+        bytes_per_launch = B * (24.0 * 75 + 4 + 4 * T) + T * (4 + 24.0 * 75)
+        cpu = {"value": cells / cpu_s, "unit": unit_name, "cores": cores, "kind": "port",
+               "sample": "first %d utterances x %d templates, %d threads" % (S, T, cores)}
+        check = lambda: bool(np.array_equal(score[:S].cpu().numpy().view(np.uint32), ref))
+        cfg = "configs[2]: 65536 utterances x %d templates, 50..100 frames each, %s" % (T, "Sakoe-Chiba DP r=10 (extension, parity unpinned)" if band else "reference greedy walk")
+    for _ in range(max(args.warmup, 3)):
+        run()
+    torch.cuda.synchronize(dev)
+    h.timing_enable(4 * args.steps + 8)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = h.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        run()
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1) / args.steps
+    recs = h.timing_collect()
+    kms = float(np.mean([m for t, m in recs if t in (1, 4, 6)])) if recs else ms
+    ach = bytes_per_launch / (kms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": unit_name, "value": units / (ms * 1e-3), "unit": unit_name, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 fixed-point", "data": "synthetic", "config": {"workload": cfg, "batch": B},
+        "utterances_per_s": B / (ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_per_launch},
+        "cpu_baseline": cpu, "parity_vs_cpu_sample": check(), "gpu_launches": h.launch_count() - l0}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +362,8 @@ def main():
     ap.add_argument("--ref-sample-per-core", type=int, default=128, help="--impl reference: utterances per core per step")
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU worker count (0 = usable cores: affinity capped by cgroup quota)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="recognise", choices=["recognise", "mfcc", "dtw", "dtw_band", "stream"])
+    ap.add_argument("--streams", type=int, default=8192)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -232,6 +371,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload != "recognise":
+        if rank == 0:
+            run_kernel_workload(args)
         return
 
     import torch

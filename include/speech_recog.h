@@ -157,6 +157,26 @@ int sr_dtw_batch_dev(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t fla
 int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
                            const sr_recog_out *out_dev);
 
+/* ---- streaming front end (stands in for record(), main.c:77-102 / ADC.C:11-103) ----------------------------
+ * n_streams concurrent captures of max_samples samples each, fed in lock-step chunks. Each push advances
+ * noise_atap (once the first n_len samples are in) and VAD frame by frame with the reference's carried state,
+ * and recognises every segment that closes (get_mfcc + dtw + argmin against the handle's bank). After the
+ * last chunk the events equal the batch results on the complete buffers; the reference itself only ever
+ * recognises segment 0 (main.c:268), here all <= 3 segments of a stream produce an event. */
+typedef struct sr_stream_pool sr_stream_pool;
+typedef struct {
+    uint32_t stream, segment;   /* which stream, which of its <= 3 segments       */
+    uint32_t start, end;        /* sample offsets of the segment                   */
+    uint32_t status;            /* SR_ST_OK or SR_ST_MFCC_FAIL                     */
+    uint32_t frm_num, best_idx, best_dis, cmd;
+} sr_stream_event;
+int sr_streams_create(sr_handle *h, uint32_t n_streams, uint32_t max_samples, uint32_t n_len, sr_stream_pool **out);
+int sr_streams_destroy(sr_stream_pool *p);
+int sr_streams_reset(sr_stream_pool *p);
+int sr_streams_push(sr_stream_pool *p, const uint16_t *chunk /* host [n_streams][chunk_stride] */, uint32_t chunk_len,
+                    uint32_t chunk_stride, sr_stream_event *events, uint32_t max_events, uint32_t *n_events);
+int sr_streams_segments(sr_stream_pool *p, uint32_t *seg_off /* [n_streams][3][2] or NULL */, atap_tag *atap /* or NULL */);
+
 /* secondary globals of the reference, batched: fft magnitudes (MFCC.C:27-62) of n frames of
  * `len` (<=1024) s16 samples each -> u32[n][512]; get_dis (DTW.C:45-62) of n row pairs. */
 int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t n, uint32_t *mag);

@@ -1,0 +1,119 @@
+// sr_internal.h -- private to the library: the handle, workspaces and launch prototypes shared by sr_api.cu
+// and sr_stream.cu. Nothing here is part of the C-ABI.
+#pragma once
+#include <mutex>
+#include <new>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "sr_common.cuh"
+
+namespace srk {
+cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad, atap_tag *atap,
+                       u32 *seg_off, int num_sms, cudaStream_t st);
+cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
+                        int num_sms, cudaStream_t st, const u32 *row_map = nullptr, u32 rows_total = 0);
+cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
+                               cudaStream_t st);
+cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st);
+cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, int band_r,
+                            u32 *score, u64 *best, int num_sms, cudaStream_t st);
+cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st);
+cudaError_t launch_best_final(const u64 *best, u32 B, u32 *best_idx, u32 *best_dis, u32 *cmd, const u8 *status,
+                              cudaStream_t st);
+cudaError_t launch_status(const u32 *seg_off, const void *ftr, u32 B, u8 *status, cudaStream_t st);
+cudaError_t launch_get_dis(const s16 *a, const s16 *b, u32 n, u32 *out, cudaStream_t st);
+cudaError_t launch_sqrt_check(u32 lo, u32 hi, unsigned long long *bad_dev, cudaStream_t st);
+}  // namespace srk
+
+using namespace srk;
+
+inline thread_local std::string g_tls_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct sr_handle {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                 // H2D of the next chunk while the current one computes
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint64_t launches = 0;
+    std::string err;
+    // template bank
+    const void *bank = nullptr;
+    DevBuf bank_own;
+    u32 n_slot = 0, slot_stride = 0;
+    // optional per-kernel timing (sr_timing_enable): event pairs recorded around every launch
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<uint32_t> ev_tag;
+    size_t ev_used = 0;
+    // grow-only device workspaces
+    DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
+};
+
+inline int fail(sr_handle *h, const char *what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+    g_tls_error = buf;
+    if (h) h->err = buf;
+    return e == cudaSuccess ? -1 : (int)e;
+}
+#define SR_CK(h, call)                                           \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return fail((h), #call, e__);    \
+    } while (0)
+#define SR_REQUIRE(h, cond)                                      \
+    do {                                                         \
+        if (!(cond)) return fail((h), "requirement failed: " #cond, cudaSuccess); \
+    } while (0)
+
+inline cudaError_t ensure(DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return cudaSuccess;
+    if (b.p) { cudaError_t e = cudaFree(b.p); b.p = nullptr; b.cap = 0; if (e != cudaSuccess) return e; }
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { b.p = nullptr; return e; }
+    b.cap = want;
+    return cudaSuccess;
+}
+
+// records a (start,end) event pair around one kernel launch when timing is enabled
+struct TimedLaunch {
+    sr_handle *h;
+    size_t slot = (size_t)-1;
+    TimedLaunch(sr_handle *hh, uint32_t tag) : h(hh) {
+        if (h->timing && (h->ev_used + 1) * 2 <= h->ev.size()) {
+            slot = h->ev_used++;
+            h->ev_tag[slot] = tag;
+            cudaEventRecord(h->ev[2 * slot], h->stream);
+        }
+    }
+    ~TimedLaunch() {
+        if (slot != (size_t)-1) cudaEventRecord(h->ev[2 * slot + 1], h->stream);
+    }
+};
+enum { TAG_VAD = 0, TAG_MFCC = 1, TAG_STATUS = 2, TAG_BEST_INIT = 3, TAG_DTW = 4, TAG_BEST_FINAL = 5, TAG_DTW_BAND = 6,
+       TAG_FFT = 7, TAG_GET_DIS = 8 };
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+
+#define H2D(h, dst, src, bytes) SR_CK(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (h)->stream))
+#define D2H(h, dst, src, bytes) SR_CK(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (h)->stream))

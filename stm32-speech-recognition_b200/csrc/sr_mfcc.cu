@@ -79,7 +79,8 @@ __device__ __forceinline__ int mfcc_frames(u32 start, u32 end, u32 U) {
 template <int kConsumerWarps>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
-                                          unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab) {
+                                          unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
+                                          const u32 *__restrict__ row_map, u32 rows_total) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MfccSmem<kConsumerWarps> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,7 +95,8 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     }
     __syncthreads();
 
-    const size_t total_bytes = (size_t)B * U * 2;
+    // row_map (streaming): utterance b's samples live in PCM row row_map[b] of a [rows_total][U] buffer
+    const size_t total_bytes = (size_t)(row_map ? rows_total : B) * U * 2;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
 
     // ================================ producer warp =============================================
@@ -112,8 +114,9 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                 continue;
             }
             // bytes [lo,hi) of the batch: samples start-1 .. start+80(F-1)+159 of utterance b
-            long long first = (long long)b * U + st - 1;           // may be -1 for b=0,start=0
-            const long long last = (long long)b * U + st + 80ll * (F - 1) + 160;   // exclusive
+            const long long row = row_map ? (long long)row_map[b] : (long long)b;
+            long long first = row * U + st - 1;                    // may be -1 for row 0, start 0
+            const long long last = row * U + st + 80ll * (F - 1) + 160;   // exclusive
             unsigned char *dst = sm.pcm[s];
             int off = 0;
             if (first < 0) {                                       // x[-1] of the whole batch: reference reads
@@ -343,8 +346,9 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                                                        const u32 *__restrict__ seg, u32 seg_stride,              \
                                                        const atap_tag *__restrict__ atap,                         \
                                                        unsigned char *__restrict__ ftr,                           \
-                                                       const DevTables *__restrict__ tab) {                      \
-        mfcc_body<W>(pcm, U, B, seg, seg_stride, atap, ftr, tab);                                                 \
+                                                       const DevTables *__restrict__ tab,                         \
+                                                       const u32 *__restrict__ row_map, u32 rows_total) {        \
+        mfcc_body<W>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total);                            \
     }
 // threads per CTA are capped at floor(65536 / regs / 128) * 128, so consumer warps + 1 producer = 16 / 20 / 24 / 28
 SR_MFCC_VARIANT(15, 128)
@@ -407,12 +411,13 @@ fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, cons
 // ---- host launchers -----------------------------------------------------------------------------
 template <int W, typename K>
 static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride,
-                                       const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st) {
+                                       const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st,
+                                       const u32 *row_map, u32 rows_total) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfccSmem<W>));
     if (e != cudaSuccess) return e;
     const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
     kern<<<grid, (W + 1) * 32, sizeof(MfccSmem<W>), st>>>(pcm, U, B, seg, seg_stride, atap,
-                                                         static_cast<unsigned char *>(ftr), tab);
+                                                         static_cast<unsigned char *>(ftr), tab, row_map, rows_total);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
@@ -425,7 +430,7 @@ static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, con
 }
 
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
-                        void *ftr, int num_sms, cudaStream_t st) {
+                        void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total) {
     if (B == 0) return cudaSuccess;
     const DevTables *tab = dev_tables();
     if (!tab) return cudaErrorInitializationError;
@@ -435,10 +440,10 @@ cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_st
         variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
     }
     switch (variant) {
-    case 23: return launch_mfcc_variant<23>(mfcc_kernel_w23, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
-    case 27: return launch_mfcc_variant<27>(mfcc_kernel_w27, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
-    default: return launch_mfcc_variant<15>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
-    case 19: return launch_mfcc_variant<19>(mfcc_kernel_w19, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st);
+    case 23: return launch_mfcc_variant<23>(mfcc_kernel_w23, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
+    case 27: return launch_mfcc_variant<27>(mfcc_kernel_w27, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
+    default: return launch_mfcc_variant<15>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
+    case 19: return launch_mfcc_variant<19>(mfcc_kernel_w19, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
     }
 }
 

@@ -30,6 +30,10 @@ class RecogOut(C.Structure):
                 ("best_idx", C.c_void_p), ("best_dis", C.c_void_p), ("cmd", C.c_void_p), ("status", C.c_void_p)]
 
 
+class StreamEvent(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("stream", "segment", "start", "end", "status", "frm_num", "best_idx", "best_dis", "cmd")]
+
+
 class ValidTag(C.Structure):
     _fields_ = [("start", C.c_void_p), ("end", C.c_void_p)]
 
@@ -60,6 +64,11 @@ def lib():
         L.sr_timing_enable.argtypes = [vp, u32]
         L.sr_timing_collect.argtypes = [vp, vp, vp, u32, vp]
         L.sr_debug_sqrt_mismatches.argtypes = [vp, u32, u32, vp]
+        L.sr_streams_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
+        L.sr_streams_destroy.argtypes = [vp]
+        L.sr_streams_reset.argtypes = [vp]
+        L.sr_streams_push.argtypes = [vp, vp, u32, u32, vp, u32, vp]
+        L.sr_streams_segments.argtypes = [vp, vp, vp]
         L.sr_set_bank.argtypes = [vp, vp, u32, u32]
         L.sr_set_bank_dev.argtypes = [vp, vp, u32, u32]
         for name in ("sr_noise_atap_batch", "sr_noise_atap_batch_dev"):
@@ -136,6 +145,9 @@ class Handle:
     # -- plumbing
     def set_stream(self, stream_ptr):
         self._ck(lib().sr_set_stream(self._h, _p(stream_ptr)))
+
+    def use_own_stream(self):
+        self._ck(lib().sr_use_own_stream(self._h))
 
     def sync(self):
         self._ck(lib().sr_sync(self._h))
@@ -248,6 +260,40 @@ class Handle:
         ro = RecogOut(*[_p(ptrs.get(k)) for k in
                         ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
         self._ck(lib().sr_recognise_batch_dev(self._h, _p(pcm_ptr), U, B, n_len, C.byref(ro)))
+
+
+class StreamPool:
+    """sr_stream_pool wrapper: lock-step chunked capture of S streams (include/speech_recog.h, streaming section)"""
+
+    def __init__(self, handle, n_streams, max_samples, n_len=2400):
+        self.h, self.S, self.L = handle, n_streams, max_samples
+        self._p = C.c_void_p()
+        handle._ck(lib().sr_streams_create(handle._h, n_streams, max_samples, n_len, C.byref(self._p)))
+        self._ev = (StreamEvent * (3 * n_streams))()
+
+    def close(self):
+        if self._p:
+            lib().sr_streams_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def reset(self):
+        self.h._ck(lib().sr_streams_reset(self._p))
+
+    def push(self, chunk, chunk_len=None, stride=None):
+        """chunk: numpy [S, chunk_len] u16 (or a raw host pointer with chunk_len/stride). Returns list of event dicts."""
+        if isinstance(chunk, np.ndarray):
+            chunk_len, stride, ptr = chunk.shape[1], chunk.strides[0] // 2, chunk.ctypes.data_as(C.c_void_p)
+        else:
+            ptr = C.c_void_p(int(chunk))
+        n = C.c_uint32(0)
+        self.h._ck(lib().sr_streams_push(self._p, ptr, chunk_len, stride, self._ev, 3 * self.S, C.byref(n)))
+        return [{k: getattr(self._ev[i], k) for k, _ in StreamEvent._fields_} for i in range(n.value)]
+
+    def segments(self):
+        seg = np.zeros((self.S, 3, 2), np.uint32)
+        atap = np.zeros(self.S, ATAP_DTYPE)
+        self.h._ck(lib().sr_streams_segments(self._p, _p(seg), _p(atap)))
+        return seg, atap
 
 
 # ---- synthetic workload (include/sr_synth.h) -------------------------------------------------------

@@ -387,6 +387,43 @@ def test_device_pointer_api_on_torch_stream(ora):
     h.close()
 
 
+@pytest.mark.parametrize("chunk", [80, 800, 777])
+def test_streaming_equals_batch(handle, ora, chunk):
+    """lock-step chunked capture (config 5 shape: 5 s streams, 3 words): the union of the streaming events equals
+    the batch VAD on the finished buffers, and every event equals get_mfcc + dtw of that segment"""
+    S, L, T = 24, 40000, 8
+    pcm = sr_b200.synth_pcm_host(S, L, 0x5EED5000, 3)
+    pcm[3] = 2048                                     # a silent stream: no event
+    bank = GOLD["synth/bank"]
+    handle.set_bank(bank, T, 4096)
+    pool = sr_b200.StreamPool(handle, S, L, 2400)
+    events, latest = [], {}
+    for n0 in range(0, L, chunk):
+        c = np.ascontiguousarray(pcm[:, n0:n0 + chunk])
+        evs = pool.push(c)
+        for e in evs:
+            # the segment closes with the chunk that delivers sample end+879 (last sample of the closing frame)
+            assert n0 <= e["end"] + 879 < n0 + c.shape[1]
+        events += evs
+    seg, atap = pool.segments()
+    pool.close()
+    batch_atap = handle.noise_atap(pcm, 2400)
+    assert atap.tobytes() == batch_atap.tobytes()
+    batch_seg = handle.vad(pcm, batch_atap)
+    assert np.array_equal(seg, batch_seg)
+    closed = [(s, k) for s in range(S) for k in range(3) if batch_seg[s, k, 1] != ob.NULL]
+    assert sorted((e["stream"], e["segment"]) for e in events) == closed and len(closed) >= 3 * (S - 1) - 2
+    for e in events:
+        s, k = e["stream"], e["segment"]
+        assert (e["start"], e["end"]) == tuple(batch_seg[s, k])
+        f = ora.mfcc_batch(pcm[s:s + 1], batch_seg[s, k].reshape(1, 2), batch_atap[s:s + 1])
+        assert e["frm_num"] == int(f["frm_num"][0]) and e["status"] == 0
+        sc, _ = ora.dtw_batch(f, bank, T, 4096, check_sign=1)
+        key = (sc[0].astype(np.uint64) << np.uint64(32)) | np.arange(T, dtype=np.uint64)
+        assert e["best_dis"] == int(key.min() >> np.uint64(32)) and e["best_idx"] == int(key.min() & np.uint64(0xFFFFFFFF))
+        assert e["cmd"] == e["best_idx"] // 4
+
+
 def test_empty_batch_and_argument_errors(handle):
     z = np.zeros((0, 8000), np.uint16)
     assert handle.recognise(z, 2400)["cmd"].shape == (0,)
