@@ -512,8 +512,26 @@ def main():
     peak, peak_src = peaks()
     ach = mfcc_bytes / (kern_ms.get("mfcc", float("nan")) * 1e-3) / 1e9
     # integer-issue view of the same kernel (the bit-exact FFT is INT32-issue bound, not HBM bound)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if B == 65536 and T == 20:                      # the capture was taken on exactly this configuration
+            traffic = [v["dram_bytes_per_launch"] for k, v in tj["kernels"].items() if k.startswith("mfcc_kernel")][0]
+            traffic_src = tj["source"]
+    except Exception:
+        pass
+    vad_bytes = (2.0 * U + 24.0) * B                    # K0: 2*U read + 24 B written per utterance
+    dtw_bytes = 24.0 * frames_rank0 + (4.0 + 4.0 * T) * B + T * 4096.0   # K2: features + scores (+ bank once)
+    other = {}
+    if kern_ms.get("vad"):
+        a = vad_bytes / (kern_ms["vad"] * 1e-3) / 1e9
+        other["vad_kernel"] = {"bound": "hbm", "achieved": a, "frac": a / peak, "algorithmic_bytes_per_launch": vad_bytes}
+    if kern_ms.get("dtw"):
+        a = dtw_bytes / (kern_ms["dtw"] * 1e-3) / 1e9
+        other["dtw_kernel"] = {"bound": "hbm", "achieved": a, "frac": a / peak, "algorithmic_bytes_per_launch": dtw_bytes}
     roofline = {"bound": "hbm", "kernel": "mfcc_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "other_kernels": other,
                 "algorithmic_bytes_per_launch": mfcc_bytes, "kernel_ms": kern_ms.get("mfcc"),
                 "kernel_share_of_step": share.get("mfcc"),
                 "note": "bit-exact fixed-point FFT: ~2000 warp instructions/frame -> INT-issue bound by design, see DESIGN.md"}
