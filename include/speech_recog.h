@@ -157,6 +157,17 @@ int sr_dtw_batch_dev(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t fla
 int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
                            const sr_recog_out *out_dev);
 
+/* save_mdl (main.c:121-138) for B utterances: noise_atap -> VAD -> get_mfcc(segment 0) -> save_ftr_mdl
+ * (Flash.C:17-67) into slot b of a flash-layout bank image bank_out[B][slot_stride] (host memory).
+ * status[b] (may be NULL): 0 save_ok / 1 VAD_fail / 2 MFCC_fail; failed slots stay erased (0xFF). */
+int sr_enrol_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, void *bank_out,
+                   uint32_t slot_stride, uint8_t *status);
+/* get_mdl + get_mean (DTW.C:195-296, defined but never called by the firmware): mdl[p] = element-wise mean of
+ * in1[p] and in2[p] along their greedy DTW path, dis[p] = step-normalised path distance; rejected pairs
+ * (2:1 length guard) return dis_err and leave mdl[p] untouched. Paths longer than 119 points are truncated
+ * (the reference writes out of bounds there). */
+int sr_get_mdl_batch(sr_handle *h, const v_ftr_tag *in1, const v_ftr_tag *in2, uint32_t n, v_ftr_tag *mdl, uint32_t *dis);
+
 /* ---- streaming front end (stands in for record(), main.c:77-102 / ADC.C:11-103) ----------------------------
  * n_streams concurrent captures of max_samples samples each, fed in lock-step chunks. Each push advances
  * noise_atap (once the first n_len samples are in) and VAD frame by frame with the reference's carried state,

@@ -200,6 +200,38 @@ uint32_t sro_dtw(const sro_ftr *fin, const sro_ftr *fmdl, uint32_t *cells) {
     return dis / step;                                               /* DTW.C:191 */
 }
 
+/* ---- DTW.C:195-296 get_mean + get_mdl (dead code in the firmware): averaged template along the walk --------
+ * Returns dis/step (SRO_DIS_ERR and mdl untouched if the guard rejects). The reference writes row `step-1` for
+ * every visited point without bound; rows >= 119 are dropped here and frm_num clamped (the reference would
+ * overrun mfcc_dat). */
+uint32_t sro_get_mdl(const sro_ftr *f1, const sro_ftr *f2, sro_ftr *fm) {
+    int I = f1->frm_num, M = f2->frm_num;
+    if (I > M * 2 || 2 * I < M) return SRO_DIS_ERR;                  /* DTW.C:231-234 */
+    const int16_t *in1 = f1->mfcc_dat, *in2 = f2->mfcc_dat;
+    int row = 0;
+    uint32_t dis = sro_get_dis(in1, in2);                            /* DTW.C:244 */
+    for (int i = 0; i < 12; ++i) fm->mfcc_dat[i] = (int16_t)((in1[i] + in2[i]) / 2);   /* DTW.C:201,245 */
+    uint16_t x = 1, y = 1, step = 1;
+    do {                                                             /* DTW.C:249-291 */
+        uint32_t up = !sro_dtw_limit(x, y + 1, I, M) ? sro_get_dis(in2 + 12, in1) : SRO_DIS_ERR;
+        uint32_t right = !sro_dtw_limit(x + 1, y, I, M) ? sro_get_dis(in2, in1 + 12) : SRO_DIS_ERR;
+        uint32_t ru = !sro_dtw_limit(x + 1, y + 1, I, M) ? sro_get_dis(in2 + 12, in1 + 12) : SRO_DIS_ERR;
+        uint32_t mn = ru;
+        if (mn > right) mn = right;
+        if (mn > up) mn = up;
+        dis += mn;
+        if (mn == ru) { in1 += 12; ++x; in2 += 12; ++y; }
+        else if (mn == up) { in2 += 12; ++y; }
+        else { in1 += 12; ++x; }
+        ++step;
+        ++row;                                                       /* mdl += mfcc_num, DTW.C:286 */
+        if (row < SRO_VV_FRM_MAX)
+            for (int i = 0; i < 12; ++i) fm->mfcc_dat[row * 12 + i] = (int16_t)((in1[i] + in2[i]) / 2);
+    } while (x < I && y < M);
+    fm->frm_num = step > SRO_VV_FRM_MAX ? SRO_VV_FRM_MAX : step;     /* DTW.C:293 */
+    return dis / step;
+}
+
 /* ---- dtw_band: NOT in the reference -- PARITY UNPINNED --------------
  * Classic DP the north_star's config[2] names: D(i,j) = d(i,j) + min(D(i-1,j), D(i,j-1), D(i-1,j-1))
  * over the Sakoe-Chiba band |j - round_down(i*M/I)| <= r (1-based i<=I, j<=M mapped 0-based below),

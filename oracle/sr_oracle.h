@@ -36,6 +36,7 @@ void     sro_mfcc(const uint16_t *pcm, uint32_t start, uint32_t end, const sro_a
 uint32_t sro_get_dis(const int16_t *a, const int16_t *b);
 int      sro_dtw_limit(int x, int y, int I, int M);
 uint32_t sro_dtw(const sro_ftr *in, const sro_ftr *mdl, uint32_t *cells);
+uint32_t sro_get_mdl(const sro_ftr *f1, const sro_ftr *f2, sro_ftr *fm);
 uint32_t sro_dtw_band(const sro_ftr *in, const sro_ftr *mdl, int r, uint32_t *cells);
 int      sro_recognise(const uint16_t *pcm, uint32_t buf_len, uint32_t n_len, const uint8_t *bank, uint32_t n_slot,
                        uint32_t slot_stride, sro_atap *atap_out, uint32_t *seg_off6, sro_ftr *ftr_out,

@@ -391,6 +391,58 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     return 0;
 }
 
+// save_mdl (main.c:121-138) for B utterances: noise_atap -> VAD -> get_mfcc(seg 0) -> save_ftr_mdl into slot b of a
+// flash-layout bank image (host memory, B x slot_stride bytes). status[b]: 0 save_ok, 1 VAD_fail, 2 MFCC_fail
+// (main.c:38-40); failed slots stay erased (0xFF). The result can be handed to sr_set_bank unchanged.
+int sr_enrol_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, void *bank_out,
+                   uint32_t slot_stride, uint8_t *status) {
+    SR_REQUIRE(h, h && (B == 0 || (pcm && bank_out)));
+    SR_REQUIRE(h, U <= 65535u && n_len <= U && slot_stride >= (uint32_t)kFtrBytes && slot_stride % 4 == 0);
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));
+    SR_CK(h, ensure(h->atap, (size_t)B * sizeof(atap_tag)));
+    SR_CK(h, ensure(h->seg, (size_t)B * 24));
+    SR_CK(h, ensure(h->ftr, (size_t)B * kFtrBytes));
+    SR_CK(h, ensure(h->status, (size_t)B));
+    SR_CK(h, ensure(h->misc0, (size_t)B * slot_stride));
+    H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
+    SR_CK(h, cudaMemsetAsync(h->atap.p, 0, (size_t)B * sizeof(atap_tag), h->stream));
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(static_cast<const u16 *>(h->pcm.p), U, B, n_len, U, 1, 1, static_cast<atap_tag *>(h->atap.p), static_cast<u32 *>(h->seg.p), h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc(static_cast<const u16 *>(h->pcm.p), U, B, static_cast<const u32 *>(h->seg.p), 6, static_cast<const atap_tag *>(h->atap.p), h->ftr.p, h->num_sms, h->stream)); }
+    SR_CK(h, launch_status(static_cast<const u32 *>(h->seg.p), h->ftr.p, B, static_cast<u8 *>(h->status.p), h->stream));
+    SR_CK(h, launch_pack_slots(h->ftr.p, static_cast<const u8 *>(h->status.p), B, h->misc0.p, slot_stride, h->stream));
+    h->launches += 4;
+    D2H(h, bank_out, h->misc0.p, (size_t)B * slot_stride);
+    if (status) D2H(h, status, h->status.p, (size_t)B);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// get_mdl (DTW.C:217-296) for n pairs: mdl[p] = average of in1[p], in2[p] along their greedy DTW path; dis[p] = the
+// path's step-normalised distance (dis_err and mdl[p] untouched when the 2:1 length guard rejects the pair).
+int sr_get_mdl_batch(sr_handle *h, const v_ftr_tag *in1, const v_ftr_tag *in2, uint32_t n, v_ftr_tag *mdl, uint32_t *dis) {
+    SR_REQUIRE(h, h && (n == 0 || (in1 && in2 && mdl)));
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)n * kFtrBytes;
+    SR_CK(h, ensure(h->misc0, bytes));
+    SR_CK(h, ensure(h->misc1, bytes));
+    SR_CK(h, ensure(h->ftr, bytes));
+    SR_CK(h, ensure(h->bdis, (size_t)n * 4));
+    H2D(h, h->misc0.p, in1, bytes);
+    H2D(h, h->misc1.p, in2, bytes);
+    H2D(h, h->ftr.p, mdl, bytes);                                   // rejected pairs leave mdl as the caller passed it
+    SR_CK(h, launch_get_mdl(h->misc0.p, h->misc1.p, h->ftr.p, n, static_cast<u32 *>(h->bdis.p), h->stream));
+    ++h->launches;
+    // like get_mfcc, get_mdl never writes save_sign: copy back bytes [2, 2860) only
+    SR_CK(h, cudaMemcpy2DAsync(reinterpret_cast<unsigned char *>(mdl) + 2, kFtrBytes, static_cast<unsigned char *>(h->ftr.p) + 2,
+                               kFtrBytes, kFtrBytes - 2, n, cudaMemcpyDeviceToHost, h->stream));
+    if (dis) D2H(h, dis, h->bdis.p, (size_t)n * 4);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t n, uint32_t *mag) {
     SR_REQUIRE(h, h && (n == 0 || (frames && mag)));
     SR_REQUIRE(h, len <= SR_FFT_POINT);                                   // MFCC.C:32-35

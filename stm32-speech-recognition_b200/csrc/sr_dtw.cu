@@ -17,58 +17,6 @@ namespace srk {
 
 constexpr int kDtwWarps = 16;
 constexpr int kTileT = 32;
-constexpr int kRowsBytes = 119 * 24;        // 2856
-
-struct __align__(16) DtwSmem {
-    unsigned char trow[kTileT][kRowsBytes];   // template rows (s16[119][12])
-    unsigned char urow[kDtwWarps][kRowsBytes];
-    u32 tnorm[kTileT][120];
-    u32 unorm[kDtwWarps][120];
-    u32 tfrm[kTileT];                         // frm_num, or 0xFFFFFFFF = slot does not take part
-};
-
-struct Row { s32 v[12]; };
-
-__device__ __forceinline__ void load_row(Row &r, const unsigned char *rows, int idx) {
-    const uint2 *p = reinterpret_cast<const uint2 *>(rows + idx * 24);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const uint2 q = p[j];
-        r.v[4 * j + 0] = (s32)lo16s(q.x); r.v[4 * j + 1] = (s32)hi16s(q.x);
-        r.v[4 * j + 2] = (s32)lo16s(q.y); r.v[4 * j + 3] = (s32)hi16s(q.y);
-    }
-}
-__device__ __forceinline__ u32 dot12(const Row &a, const Row &b) {
-    u32 s = 0;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s += (u32)a.v[j] * (u32)b.v[j];
-    return s;
-}
-// get_dis, DTW.C:45-62, from the precomputed squared norms
-__device__ __forceinline__ u32 dist(const Row &a, u32 na, const Row &b, u32 nb) {
-    return usqrt_trunc(na + nb - 2u * dot12(a, b));
-}
-// dtw_limit, DTW.C:76-109: true = "ins"
-__device__ __forceinline__ bool inside(int x, int y, int X1, int X2, int I, int M) {
-    x &= 0xFFFF; y &= 0xFFFF;
-    const bool out_a = (x < X1) ? (y >= 2 * x + 2) : (2 * y + I - 2 * M >= x + 4);
-    const bool out_b = (x < X2) ? (2 * y + 2 <= x) : (y + 4 <= 2 * x + M - 2 * I);
-    return !(out_a || out_b);
-}
-
-__device__ __forceinline__ void stage_rows(unsigned char *dst, u32 *norm, const unsigned char *src_ftr, int nrows,
-                                           int lane, int nlanes) {
-    // src_ftr points at a v_ftr_tag (4-byte aligned); rows start at +4
-    const u32 *s = reinterpret_cast<const u32 *>(src_ftr + 4);
-    u32 *d = reinterpret_cast<u32 *>(dst);
-    for (int i = lane; i < nrows * 6; i += nlanes) d[i] = s[i];
-}
-__device__ __forceinline__ void row_norms(const unsigned char *rows, u32 *norm, int nrows, int lane, int nlanes) {
-    for (int r = lane; r < nrows; r += nlanes) {
-        Row t; load_row(t, rows, r);
-        norm[r] = dot12(t, t);
-    }
-}
 
 // ---- byte-plane rows: 6 words = lo bytes of dims 0..11 (3 words) then hi bytes (3 words) -----------------
 constexpr int kSlotBytes = 119 * 24 + 120 * 4;            // rows + squared norms = 3336
@@ -265,6 +213,83 @@ cudaError_t launch_sqrt_check(u32 lo, u32 hi, unsigned long long *bad_dev, cudaS
     return cudaGetLastError();
 }
 
+// ---- get_mdl / get_mean (DTW.C:195-296): the reference's (never called) template averaging ----------------
+// Same greedy walk as dtw() between two feature sets; every visited point (x,y) emits the element-wise mean
+// (a+b)/2 (C truncation, DTW.C:201) of in1[x-1] and in2[y-1] as the next row of the model; frm_num = number of
+// points, return value dis/step. One thread per pair (not a hot path). The reference writes past mfcc_dat when
+// the path is longer than vv_frm_max rows; here rows beyond 118 are dropped and frm_num is clamped to 119.
+__device__ __forceinline__ u32 get_dis_rows(const s16 *a, const s16 *b) {
+    u32 d = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { const s32 dif = (s32)a[j] - (s32)b[j]; d += (u32)dif * (u32)dif; }
+    return usqrt_trunc(d);
+}
+__device__ __forceinline__ bool ins_xy(int x, int y, int X1, int X2, int I, int M) {
+    const bool out_a = (x < X1) ? (y >= 2 * x + 2) : (2 * y + I - 2 * M >= x + 4);
+    const bool out_b = (x < X2) ? (2 * y + 2 <= x) : (y + 4 <= 2 * x + M - 2 * I);
+    return !(out_a || out_b);
+}
+__global__ void get_mdl_kernel(const unsigned char *in1, const unsigned char *in2, unsigned char *mdl, u32 n, u32 *dis_out) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned char *f1 = in1 + (size_t)p * kFtrBytes, *f2 = in2 + (size_t)p * kFtrBytes;
+    unsigned char *fm = mdl + (size_t)p * kFtrBytes;
+    const int I = (int)(*reinterpret_cast<const u16 *>(f1 + 2)), M = (int)(*reinterpret_cast<const u16 *>(f2 + 2));
+    if (I > M * 2 || 2 * I < M || I > 119 || M > 119) { dis_out[p] = SR_DIS_ERR; return; }      // DTW.C:231-234: mdl untouched
+    const s16 *a = reinterpret_cast<const s16 *>(f1 + 4), *b = reinterpret_cast<const s16 *>(f2 + 4);
+    s16 *m = reinterpret_cast<s16 *>(fm + 4);
+    const int X1 = (2 * M - I) / 3, X2 = (4 * I - 2 * M) / 3;
+    auto mean_row = [&](int row, const s16 *ra, const s16 *rb) {
+        if (row >= 119) return;
+        for (int j = 0; j < 12; ++j) m[row * 12 + j] = (s16)(((s32)ra[j] + (s32)rb[j]) / 2);
+    };
+    u32 dis = get_dis_rows(a, b);
+    mean_row(0, a, b);
+    int x = 1, y = 1;
+    u32 step = 1;
+    do {
+        const u32 up = ins_xy(x, y + 1, X1, X2, I, M) ? get_dis_rows(b + 12 * y, a + 12 * (x - 1)) : SR_DIS_ERR;
+        const u32 right = ins_xy(x + 1, y, X1, X2, I, M) ? get_dis_rows(b + 12 * (y - 1), a + 12 * x) : SR_DIS_ERR;
+        const u32 ru = ins_xy(x + 1, y + 1, X1, X2, I, M) ? get_dis_rows(b + 12 * y, a + 12 * x) : SR_DIS_ERR;
+        u32 mn = ru;
+        if (mn > right) mn = right;
+        if (mn > up) mn = up;
+        dis += mn;
+        if (mn == ru) { ++x; ++y; } else if (mn == up) { ++y; } else { ++x; }
+        mean_row((int)step, a + 12 * (x - 1), b + 12 * (y - 1));                                   // DTW.C:286-287
+        ++step;
+    } while (x < I && y < M);
+    *reinterpret_cast<u16 *>(fm + 2) = (u16)min(step, 119u);                                         // DTW.C:293
+    dis_out[p] = dis / step;
+}
+
+// ---- save_ftr_mdl (Flash.C:17-67) for a batch: flash-layout slots from freshly computed features -------------
+__global__ void pack_slots_kernel(const unsigned char *ftr, const u8 *status, u32 B, unsigned char *bank, u32 slot_stride) {
+    const u32 b = blockIdx.x;
+    if (b >= B) return;
+    u32 *dst = reinterpret_cast<u32 *>(bank + (size_t)b * slot_stride);
+    const u32 *src = reinterpret_cast<const u32 *>(ftr + (size_t)b * kFtrBytes);
+    const bool ok = status[b] == SR_ST_OK;
+    const u32 frm = src[0] >> 16;
+    const u32 used = ok ? 1u + 6u * frm : 0u;                      // header word + 6 words per row (Flash.C:27,56-63)
+    for (u32 i = threadIdx.x; i < slot_stride / 4; i += blockDim.x) {
+        u32 v = 0xFFFFFFFFu;                                       // erased flash (Flash.C:32-39)
+        if (i < used) v = i == 0 ? ((frm << 16) | SR_SAVE_MASK) : src[i];
+        dst[i] = v;
+    }
+}
+cudaError_t launch_get_mdl(const void *in1, const void *in2, void *mdl, u32 n, u32 *dis, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    get_mdl_kernel<<<(n + 63) / 64, 64, 0, st>>>(static_cast<const unsigned char *>(in1), static_cast<const unsigned char *>(in2),
+                                                static_cast<unsigned char *>(mdl), n, dis);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_slots(const void *ftr, const u8 *status, u32 B, void *bank, u32 slot_stride, cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    pack_slots_kernel<<<B, 128, 0, st>>>(static_cast<const unsigned char *>(ftr), status, B, static_cast<unsigned char *>(bank), slot_stride);
+    return cudaGetLastError();
+}
+
 // get_dis for n independent row pairs (secondary drop-in symbol, DTW.C:45-62)
 __global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,54 +385,44 @@ __global__ void __launch_bounds__(kDtwWarps * 32)
 dtw_band_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
                 u32 slot_stride, u32 flags, int r, u32 *__restrict__ score, u64 *__restrict__ best) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    DtwSmem &sm = *reinterpret_cast<DtwSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 t0 = blockIdx.x * kTileT;
-    for (int tt = warp; tt < kTileT; tt += kDtwWarps) {
-        const u32 t = t0 + tt;
-        u32 frm = 0xFFFFFFFFu;
-        if (t < T) {
-            const unsigned char *slot = bank + (size_t)t * slot_stride;
-            const u32 hdr = *reinterpret_cast<const u32 *>(slot);
-            frm = hdr >> 16;
-            if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;
-            const int nrows = (frm == 0xFFFFFFFFu) ? 0 : (int)min(frm, 119u);
-            stage_rows(sm.trow[tt], sm.tnorm[tt], slot, nrows, lane, 32);
-            __syncwarp();
-            row_norms(sm.trow[tt], sm.tnorm[tt], nrows, lane, 32);
-        }
-        if (lane == 0) sm.tfrm[tt] = frm;
+    const int Tt = (int)min((u32)kTileT, T - t0);
+    unsigned char *tile = smem_raw;                                               // byte-plane slots, as in dtw_kernel
+    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)kTileT * kSlotBytes);
+    unsigned char *uslot = smem_raw + (size_t)kTileT * kSlotBytes + 128 + (size_t)warp * kSlotBytes;
+    for (int tt = warp; tt < Tt; tt += kDtwWarps) {
+        const unsigned char *slot = bank + (size_t)(t0 + tt) * slot_stride;
+        const u32 hdr = *reinterpret_cast<const u32 *>(slot);
+        u32 frm = hdr >> 16;
+        if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;
+        if (frm > 119u) frm = 0xFFFFFFFFu;
+        stage_planes(tile + (size_t)tt * kSlotBytes, slot, frm == 0xFFFFFFFFu ? 0 : (int)frm, lane, 32);
+        if (lane == 0) tfrm[tt] = frm;
     }
     __syncthreads();
-    unsigned char *urow = sm.urow[warp];
-    u32 *unorm = sm.unorm[warp];
     for (u32 u = blockIdx.y * kDtwWarps + warp; u < B; u += gridDim.y * kDtwWarps) {
         const unsigned char *uf = in_ftr + (size_t)u * kFtrBytes;
         const int I = (int)((*reinterpret_cast<const u32 *>(uf)) >> 16);
         __syncwarp();
-        const int nrows = min(I, 119);
-        stage_rows(urow, unorm, uf, nrows, lane, 32);
-        __syncwarp();
-        row_norms(urow, unorm, nrows, lane, 32);
+        if (I <= 119) stage_planes(uslot, uf, I, lane, 32);
         __syncwarp();
         u32 my_result = SR_DIS_ERR;                       // lane tt keeps the result of template tt
-        for (int tt = 0; tt < kTileT; ++tt) {
-            const u32 Mraw = sm.tfrm[tt];
-            if (t0 + tt >= T) break;
+        for (int tt = 0; tt < Tt; ++tt) {
+            const u32 Mraw = tfrm[tt];
             const int M = (int)Mraw;
             u32 result = SR_DIS_ERR;
-            if (Mraw != 0xFFFFFFFFu && I >= 1 && M >= 1 && I <= 119 && M <= 119 && !(I > M * 2 || 2 * I < M)) {
-                const unsigned char *trow = sm.trow[tt];
-                const u32 *tnorm = sm.tnorm[tt];
+            if (Mraw != 0xFFFFFFFFu && I >= 1 && M >= 1 && I <= 119 && !(I > M * 2 || 2 * I < M)) {
+                const unsigned char *trow = tile + (size_t)tt * kSlotBytes;
                 s32 Dprev = kInf;
                 int cprev = 0;
                 for (int i = 0; i < I; ++i) {
                     const int c = (i * M) / I, j = c - r + lane;
                     const bool valid = lane <= 2 * r && j >= 0 && j < M;
-                    Row a, b;
-                    load_row(a, urow, i);                                     // broadcast read
-                    s32 d = 0;
-                    if (valid) { load_row(b, trow, j); d = (s32)dist(a, unorm[i], b, tnorm[j]); }
+                    PRow a, b;
+                    load_prow(a, uslot, i);                                   // broadcast read
+                    load_prow(b, trow, valid ? j : 0);
+                    const s32 d = valid ? (s32)pdist(a, b) : 0;
                     const int sft = c - cprev;
                     const int su = lane + sft, sd = lane + sft - 1;
                     s32 up = __shfl_sync(0xFFFFFFFFu, Dprev, su & 31);
@@ -449,7 +464,8 @@ cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, 
                             u32 *score, u64 *best, int num_sms, cudaStream_t st) {
     if (B == 0 || T == 0) return cudaSuccess;
     if (band_r < 0 || band_r > 15) return cudaErrorInvalidValue;               // 2r+1 lanes of one warp
-    cudaError_t e = cudaFuncSetAttribute(dtw_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DtwSmem));
+    const size_t band_smem = (size_t)kTileT * kSlotBytes + 128 + (size_t)kDtwWarps * kSlotBytes;
+    cudaError_t e = cudaFuncSetAttribute(dtw_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_smem);
     if (e != cudaSuccess) return e;
     const u32 tiles = (T + kTileT - 1) / kTileT;
     u32 gy = ((u32)num_sms + tiles - 1) / tiles;
@@ -458,7 +474,7 @@ cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, 
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
     dim3 grid(tiles, gy);
-    dtw_band_kernel<<<grid, kDtwWarps * 32, sizeof(DtwSmem), st>>>(static_cast<const unsigned char *>(in_ftr), B,
+    dtw_band_kernel<<<grid, kDtwWarps * 32, band_smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
                                                                   static_cast<const unsigned char *>(bank), T,
                                                                   slot_stride, flags, band_r, score, best);
     return cudaGetLastError();

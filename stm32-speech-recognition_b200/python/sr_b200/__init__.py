@@ -64,6 +64,8 @@ def lib():
         L.sr_timing_enable.argtypes = [vp, u32]
         L.sr_timing_collect.argtypes = [vp, vp, vp, u32, vp]
         L.sr_debug_sqrt_mismatches.argtypes = [vp, u32, u32, vp]
+        L.sr_enrol_batch.argtypes = [vp, vp, u32, u32, u32, vp, u32, vp]
+        L.sr_get_mdl_batch.argtypes = [vp, vp, vp, u32, vp, vp]
         L.sr_streams_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
         L.sr_streams_destroy.argtypes = [vp]
         L.sr_streams_reset.argtypes = [vp]
@@ -224,6 +226,21 @@ class Handle:
                         ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
         self._ck(lib().sr_recognise_batch(self._h, _p(pcm), U, B, n_len, C.byref(ro)))
         return out
+
+    def enrol(self, pcm, n_len=2400, slot_stride=4096):
+        B, U = pcm.shape
+        bank = np.zeros((B, slot_stride), np.uint8)
+        status = np.zeros(B, np.uint8)
+        self._ck(lib().sr_enrol_batch(self._h, _p(pcm), U, B, n_len, _p(bank), slot_stride, _p(status)))
+        return bank, status
+
+    def get_mdl(self, in1, in2, mdl=None):
+        n = in1.shape[0]
+        if mdl is None:
+            mdl = np.zeros(n, FTR_DTYPE)
+        dis = np.zeros(n, np.uint32)
+        self._ck(lib().sr_get_mdl_batch(self._h, _p(in1), _p(in2), n, _p(mdl), _p(dis)))
+        return mdl, dis
 
     def fft_mag(self, frames):
         n, length = frames.shape

@@ -89,6 +89,14 @@ class PortOracle(_Base):
     def get_dis(self, a, b):
         return np.array([self.lib.sro_get_dis(_p(a[i]), _p(b[i])) for i in range(a.shape[0])], np.uint32)
 
+    def get_mdl(self, f1, f2):
+        self.lib.sro_get_mdl.restype = C.c_uint32
+        n = f1.shape[0]
+        mdl, dis = np.zeros(n, FTR_DTYPE), np.zeros(n, np.uint32)
+        for i in range(n):
+            dis[i] = self.lib.sro_get_mdl(_p(f1[i:i + 1]), _p(f2[i:i + 1]), _p(mdl[i:i + 1]))
+        return mdl, dis
+
     def dtw_batch(self, ftr_in, bank, n_slot, slot_stride, check_sign=0, band_r=-1, nthreads=1):
         B = ftr_in.shape[0]
         score = np.zeros((B, n_slot), np.uint32)
@@ -157,6 +165,15 @@ class RefOracle(_Base):
 
     def get_dis(self, a, b):
         return np.array([self.lib.get_dis(_p(a[i]), _p(b[i])) for i in range(a.shape[0])], np.uint32)
+
+    def get_mdl(self, f1, f2):
+        """the reference's own get_mdl (DTW.C:217); only safe for paths of <= 119 points (it does not bound its writes)"""
+        self.lib.get_mdl.restype = C.c_uint32
+        n = f1.shape[0]
+        mdl, dis = np.zeros(n, FTR_DTYPE), np.zeros(n, np.uint32)
+        for i in range(n):
+            dis[i] = self.lib.get_mdl(_p(f1[i:i + 1]), _p(f2[i:i + 1]), _p(mdl[i:i + 1]))
+        return mdl, dis
 
     def dtw_batch(self, ftr_in, bank, n_slot, slot_stride, check_sign=0, band_r=-1, nthreads=1):
         assert band_r < 0, "the reference has no banded DP"

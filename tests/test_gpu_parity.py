@@ -387,6 +387,32 @@ def test_device_pointer_api_on_torch_stream(ora):
     h.close()
 
 
+def test_enrol_and_get_mdl(handle, ora):
+    """save_mdl (main.c:121-138 + Flash.C:17-67) as a batch, and the reference's template averaging get_mdl"""
+    B, U = 40, 8000
+    pcm = sr_b200.synth_pcm_host(B, U, 0x7E3A0000)
+    pcm[5] = 2048                                     # VAD_fail: slot stays erased
+    bank, status = handle.enrol(pcm, 2400)
+    ref = ora.recognise_batch(pcm, 2400, None, 0, 4096)
+    assert np.array_equal(status, ref["status"]) and status[5] == 1
+    want = sr_b200.make_bank(ref["ftr"])
+    want[ref["status"] != 0] = 0xFF                   # save_ftr_mdl is never reached: the slot stays erased
+    assert np.array_equal(bank, want) and (bank[5] == 0xFF).all()
+    f1 = sr_b200.synth_ftr_host(64, 0xAA00, 1, 59).view(sr_b200.FTR_DTYPE).reshape(-1)
+    f2 = sr_b200.synth_ftr_host(64, 0xBB00, 1, 59).view(sr_b200.FTR_DTYPE).reshape(-1)
+    want_m, want_d = ora.get_mdl(f1, f2)
+    pre = np.zeros(64, sr_b200.FTR_DTYPE)
+    pre["save_sign"] = 777
+    got_m, got_d = handle.get_mdl(f1, f2, pre)
+    assert np.array_equal(got_d, want_d) and ob.ftr_equal(got_m, want_m) and (got_m["save_sign"] == 777).all()
+    # long paths: frm_num clamps at 119 instead of the reference's out-of-bounds writes (port == kernel)
+    g1 = sr_b200.synth_ftr_host(16, 0xCC00, 100, 119).view(sr_b200.FTR_DTYPE).reshape(-1)
+    g2 = sr_b200.synth_ftr_host(16, 0xDD00, 100, 119).view(sr_b200.FTR_DTYPE).reshape(-1)
+    pm, pd = ob.port().get_mdl(g1, g2)
+    gm, gd = handle.get_mdl(g1, g2)
+    assert np.array_equal(gd, pd) and ob.ftr_equal(gm, pm) and (gm["frm_num"] == 119).any()
+
+
 @pytest.mark.parametrize("chunk", [80, 800, 777])
 def test_streaming_equals_batch(handle, ora, chunk):
     """lock-step chunked capture (config 5 shape: 5 s streams, 3 words): the union of the streaming events equals

@@ -100,6 +100,15 @@ def test_port_dtw_equals_reference_build_on_random_features():
     assert (a == ob.NULL).any() and (a != ob.NULL).any()          # the 2:1 guard fires on some pairs
 
 
+@need_ref
+def test_port_get_mdl_equals_reference_build():
+    f1 = sr_b200.synth_ftr_host(40, 0xAA00, 1, 59).view(ob.FTR_DTYPE).reshape(-1)        # paths <= 117 points: the
+    f2 = sr_b200.synth_ftr_host(40, 0xBB00, 1, 59).view(ob.FTR_DTYPE).reshape(-1)        # reference does not bound its writes
+    m1, d1 = ob.ref().get_mdl(f1, f2)
+    m2, d2 = ob.port().get_mdl(f1, f2)
+    assert np.array_equal(d1, d2) and ob.ftr_equal(m1, m2) and (d1 != ob.NULL).any() and (d1 == ob.NULL).any()
+
+
 def test_dtw_band_oracle_properties():
     """dtw_band is our own extension (parity unpinned by the reference): sanity properties only"""
     raw = sr_b200.synth_ftr_host(6, 0xD7A20000, 50, 100)
