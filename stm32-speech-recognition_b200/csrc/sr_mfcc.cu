@@ -104,7 +104,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
         int it = 0;
         for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it) {
             const int s = it % kNBuf;
-            if (it >= kNBuf) mbar_wait(&sm.empty[s], ((it / kNBuf) - 1) & 1);
+            if (it >= kNBuf) mbar_wait_relaxed(&sm.empty[s], ((it / kNBuf) - 1) & 1);
             const u32 st = seg[(size_t)b * seg_stride], en = seg[(size_t)b * seg_stride + 1];
             const int F = mfcc_frames(st, en, U);
             const u32 mid = atap[b].mid_val;
