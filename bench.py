@@ -358,7 +358,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="utterances per GPU per step")
     ap.add_argument("--templates", type=int, default=20)
-    ap.add_argument("--cpu-sample-per-core", type=int, default=512, help="cpu_baseline leg of the B200 arm (one shot)")
+    ap.add_argument("--cpu-sample-per-core", type=int, default=4096, help="cpu_baseline leg of the B200 arm (one shot)")
     ap.add_argument("--ref-sample-per-core", type=int, default=128, help="--impl reference: utterances per core per step")
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU worker count (0 = usable cores: affinity capped by cgroup quota)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
