@@ -460,10 +460,162 @@ dtw_band_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned 
     }
 }
 
+// ---- K3b: the same banded DP, one THREAD per pair, band in registers (compile-time radius) -----------------------
+// 3.7x fewer issue slots per lattice cell than the warp-scan form: no scans, no idle lanes (21 of 32), lane packing
+// and byte-plane dp4a distances exactly like dtw_kernel. The band of row i sits at columns c_i-R..c_i+R with
+// c_i = floor(i*M/I); it slides by s = c_i - c_{i-1} in {0,1,2} per row, realised as two predicated shift-by-one
+// passes over the register array (no divergence between lanes whose templates have different lengths).
+template <int R>
+__global__ void __launch_bounds__(kDtwWarps * 32)
+dtw_band_thread_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
+                       u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best, int Wg, int NU, int G,
+                       u32 tile0) {
+    constexpr int W = 2 * R + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 t0 = (blockIdx.x + tile0) * kTileT;
+    const int Tt = (int)min((u32)kTileT, T - t0);
+    unsigned char *tile = smem_raw;
+    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)kTileT * kSlotBytes);
+    unsigned char *uslots = smem_raw + (size_t)kTileT * kSlotBytes + 128;
+    u32 *ufrm = reinterpret_cast<u32 *>(uslots + (size_t)G * NU * kSlotBytes);
+    for (int tt = warp; tt < Tt; tt += kDtwWarps) {
+        const unsigned char *slot = bank + (size_t)(t0 + tt) * slot_stride;
+        const u32 hdr = *reinterpret_cast<const u32 *>(slot);
+        u32 frm = hdr >> 16;
+        if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;
+        if (frm > 119u) frm = 0xFFFFFFFFu;
+        stage_planes(tile + (size_t)tt * kSlotBytes, slot, frm == 0xFFFFFFFFu ? 0 : (int)frm, lane, 32);
+        if (lane == 0) tfrm[tt] = frm;
+    }
+    __syncthreads();
+    const int group = warp / Wg, wig = warp - group * Wg;
+    if (group >= G) return;
+    const int gthreads = Wg * 32, gtid = wig * 32 + lane;
+    const int ul = gtid / Tt, tl = gtid - ul * Tt;
+    const bool lane_has_pair = ul < NU;
+    unsigned char *gslots = uslots + (size_t)group * NU * kSlotBytes;
+    u32 *gfrm = ufrm + group * NU;
+    const unsigned char *trow = tile + (size_t)tl * kSlotBytes;
+    const u32 Mraw = lane_has_pair ? tfrm[tl] : 0xFFFFFFFFu;
+    const u32 t = t0 + (u32)tl;
+    for (u32 ubase = (blockIdx.y * G + group) * NU; ubase < B; ubase += gridDim.y * G * NU) {
+        for (int sl = 0; sl < NU; ++sl) {
+            const u32 u = ubase + sl;
+            u32 frm = 0xFFFFFFFFu;
+            if (u < B) {
+                const unsigned char *uf = in_ftr + (size_t)u * kFtrBytes;
+                frm = (*reinterpret_cast<const u32 *>(uf)) >> 16;
+                if (frm > 119u) frm = 0xFFFFFFFFu;
+                else stage_planes(gslots + (size_t)sl * kSlotBytes, uf, (int)frm, gtid, gthreads);
+            }
+            if (gtid == 0) gfrm[sl] = frm;
+        }
+        group_barrier(1 + group, gthreads);
+        const u32 u = ubase + (u32)ul;
+        if (lane_has_pair && u < B) {
+            const u32 Iraw = gfrm[ul];
+            const int I = (int)Iraw, M = (int)Mraw;
+            u32 result = SR_DIS_ERR;
+            if (Iraw != 0xFFFFFFFFu && Mraw != 0xFFFFFFFFu && I >= 1 && M >= 1 && !(I > M * 2 || 2 * I < M)) {
+                const unsigned char *urow = gslots + (size_t)ul * kSlotBytes;
+                s32 D[W];
+#pragma unroll
+                for (int k = 0; k < W; ++k) D[k] = kInf;
+                int c = 0, cprev = 0, err = 0;                     // c = floor(i*M/I) kept incrementally: i*M = c*I + err
+                for (int i = 0; i < I; ++i) {
+                    const int sft = c - cprev;                     // 0, 1 or 2 (M <= 2I)
+                    // diag source of cell k=0 is the old element at index sft-1
+                    s32 dm1 = sft == 2 ? D[1] : (sft == 1 ? D[0] : kInf);
+                    if (sft >= 1) {
+#pragma unroll
+                        for (int k = 0; k < W - 1; ++k) D[k] = D[k + 1];
+                        D[W - 1] = kInf;
+                    }
+                    if (sft >= 2) {
+#pragma unroll
+                        for (int k = 0; k < W - 1; ++k) D[k] = D[k + 1];
+                        D[W - 1] = kInf;
+                    }
+                    PRow a;
+                    load_prow(a, urow, i);
+                    s32 left = kInf;
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        const int j = c - R + k;
+                        const bool valid = j >= 0 && j < M;
+                        const s32 up = D[k];
+                        s32 bst = min(min(up, dm1), left);
+                        if (i == 0 && j == 0) bst = 0;
+                        PRow b;
+                        load_prow(b, trow, valid ? j : 0);
+                        const s32 d = (s32)pdist(a, b);
+                        const s32 x = (valid && bst < kInf / 2) ? bst + d : kInf;
+                        dm1 = up;                                  // becomes the diagonal source of cell k+1
+                        D[k] = x;
+                        left = x;
+                    }
+                    cprev = c;
+                    err += M;                                      // advance c to floor((i+1)*M/I)
+                    if (err >= I) { err -= I; ++c; }
+                    if (err >= I) { err -= I; ++c; }
+                }
+                const int kend = (M - 1) - (cprev - R);            // cell holding column M-1 in the last row
+                s32 fin = kInf;
+#pragma unroll
+                for (int k = 0; k < W; ++k) if (k == kend) fin = D[k];
+                if (fin < kInf / 2) result = (u32)fin / (u32)(I + M);
+            }
+            if (score) score[(size_t)u * T + t] = result;
+            if (best) atomicMin(reinterpret_cast<unsigned long long *>(&best[u]), (unsigned long long)(((u64)result << 32) | (u64)t));
+        }
+        group_barrier(1 + group, gthreads);
+    }
+}
+
+static cudaError_t launch_band_thread_tiles(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags,
+                                            u32 *score, u64 *best, int num_sms, cudaStream_t st, u32 tile0, u32 ntiles, int Tt) {
+    const size_t budget = 224 * 1024 - (size_t)kTileT * kSlotBytes - 128 - 256;
+    const int slots_max = (int)(budget / kSlotBytes);
+    int bestWg = 1, bestNU = 1, bestG = kDtwWarps;
+    double best_util = -1.0;
+    for (int Wg = 1; Wg <= 8; ++Wg) {
+        const int NU = (32 * Wg) / Tt;
+        if (NU < 1) continue;
+        int G = kDtwWarps / Wg;
+        if (G > slots_max / NU) G = slots_max / NU;
+        if (G < 1) continue;
+        const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kDtwWarps);
+        if (util > best_util + 1e-9) { best_util = util; bestWg = Wg; bestNU = NU; bestG = G; }
+    }
+    const size_t smem = (size_t)kTileT * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
+    cudaError_t e = cudaFuncSetAttribute(dtw_band_thread_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return e;
+    u32 gy = ((u32)num_sms + ntiles - 1) / ntiles;
+    const u32 ugroups = (B + (u32)(bestG * bestNU) - 1) / (u32)(bestG * bestNU);
+    if (gy > ugroups) gy = ugroups;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid(ntiles, gy);
+    dtw_band_thread_kernel<10><<<grid, kDtwWarps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
+                                                                  static_cast<const unsigned char *>(bank), T, slot_stride,
+                                                                  flags, score, best, bestWg, bestNU, bestG, tile0);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, int band_r,
                             u32 *score, u64 *best, int num_sms, cudaStream_t st) {
     if (B == 0 || T == 0) return cudaSuccess;
     if (band_r < 0 || band_r > 15) return cudaErrorInvalidValue;               // 2r+1 lanes of one warp
+    if (band_r == 10) {                                                       // the BASELINE radius: thread-per-pair form
+        const u32 full = T / kTileT, rem = T % kTileT;
+        if (full) {
+            cudaError_t e1 = launch_band_thread_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, num_sms, st, 0, full, kTileT);
+            if (e1 != cudaSuccess) return e1;
+        }
+        if (rem) return launch_band_thread_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, num_sms, st, full, 1, (int)rem);
+        return cudaSuccess;
+    }
     const size_t band_smem = (size_t)kTileT * kSlotBytes + 128 + (size_t)kDtwWarps * kSlotBytes;
     cudaError_t e = cudaFuncSetAttribute(dtw_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_smem);
     if (e != cudaSuccess) return e;
