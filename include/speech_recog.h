@@ -90,7 +90,9 @@ uint32_t  dtw(v_ftr_tag *ftr_in, v_ftr_tag *frt_mdl);
 uint32_t *fft(int16_t *dat_buf, uint16_t buf_len);        /* returns a thread-local u32[1024]; [0,512) valid */
 uint32_t  get_dis(int16_t *frm_ftr1, int16_t *frm_ftr2);
 
-/* ---- (2) batched handle API ----------------------------------------------------------------- */
+/* ---- (2) batched handle API -----------------------------------------------------------------
+ * A handle owns its device workspaces and stream; use one handle per thread (calls on the same handle must not
+ * overlap). Different handles -- on the same or on different GPUs -- are independent. */
 typedef struct sr_handle sr_handle;
 
 int         sr_create(int device, sr_handle **out);       /* device ordinal; <0 = current device     */

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "../../include/sr_synth.h"
@@ -121,8 +122,10 @@ extern "C" int sr_synth_pcm_dev(uint16_t *pcm_dev, uint32_t U, uint32_t B, uint6
                                 void *cuda_stream) {
     if (B == 0) return 0;
     static int16_t *tab_dev[64] = {nullptr};
+    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lk(mu);
     if (!tab_dev[dev]) {
         if (cudaMalloc(&tab_dev[dev], sizeof(sr_synth_sine)) != cudaSuccess) return -1;
         if (cudaMemcpy(tab_dev[dev], sr_synth_sine, sizeof(sr_synth_sine), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
