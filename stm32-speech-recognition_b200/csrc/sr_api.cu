@@ -334,8 +334,9 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     const size_t T = h->n_slot;
-    // chunk: ~128 MB of PCM, a multiple of 8 utterances (keeps every chunk base 16-byte aligned)
-    uint32_t chunk = (uint32_t)(((size_t)128 << 20) / ((size_t)U * 2));
+    // chunk: ~32 MB of PCM (measured best of 16..256 MB on B200; SR_CHUNK_MB overrides), a multiple of 8 utterances (keeps every chunk base 16-byte aligned)
+    static const size_t chunk_mb = [] { const char *e = getenv("SR_CHUNK_MB"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 32); }();
+    uint32_t chunk = (uint32_t)((chunk_mb << 20) / ((size_t)U * 2));
     chunk = chunk < 8 ? 8 : (chunk & ~7u);
     if (chunk > B) chunk = B;
     const uint32_t nchunks = (B + chunk - 1) / chunk;

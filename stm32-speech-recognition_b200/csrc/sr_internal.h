@@ -4,6 +4,7 @@
 #include <mutex>
 #include <new>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
