@@ -450,6 +450,16 @@ def test_streaming_equals_batch(handle, ora, chunk):
         assert e["cmd"] == e["best_idx"] // 4
 
 
+def test_thin_c_host_links_reference_named_symbols():
+    """host/spch_host.c = save_mdl + spch_recg transcribed against the reference's headers (include/compat) and linked
+    straight against libspeech_b200.so: single-call path and batched path must agree"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "stm32-speech-recognition_b200", "host", "spch_host")
+    assert os.path.exists(exe), "host binary not built (see __graft_entry__.build)"
+    r = subprocess.run([exe, "20"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:]
+
+
 def test_empty_batch_and_argument_errors(handle):
     z = np.zeros((0, 8000), np.uint16)
     assert handle.recognise(z, 2400)["cmd"].shape == (0,)
