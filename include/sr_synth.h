@@ -13,6 +13,7 @@
  *   noise-only samples would follow it; clip to [0,4095]. */
 #ifndef SR_SYNTH_H_
 #define SR_SYNTH_H_
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -25,6 +26,11 @@ int sr_synth_pcm_dev(uint16_t *pcm_dev, uint32_t U, uint32_t B, uint64_t seed_ba
  * [fmin,fmax], mfcc ~ clipped +-3000 triangular-ish noise of scale 600 with +400 on c0;
  * out = B structs of `stride` bytes (>= 2860), save_sign = 12345. Host only. */
 int sr_synth_ftr_host(void *out, uint32_t stride, uint32_t B, uint64_t seed_base, uint32_t fmin, uint32_t fmax);
+/* WAV ingestion: RIFF/WAVE PCM, 8-bit unsigned or 16-bit signed, mono or interleaved (channel 0 is
+ * taken) -> the 12-bit unsigned ADC codes the path consumes: 16-bit x -> x/16 + 2048 (C truncation), 8-bit
+ * x -> (x-128)*16 + 2048. Host only (input adaptation, like the generator above). Returns the number of samples
+ * written (<= max_samples), or -1 on a malformed / unsupported file; *sample_rate receives the file's rate. */
+long sr_wav_to_adc12(const void *wav, size_t wav_bytes, uint16_t *out, size_t max_samples, uint32_t *sample_rate);
 #ifdef __cplusplus
 }
 #endif

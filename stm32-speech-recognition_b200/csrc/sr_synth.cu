@@ -157,3 +157,37 @@ extern "C" int sr_synth_ftr_host(void *out, uint32_t stride, uint32_t B, uint64_
     }
     return 0;
 }
+
+// ---- WAV -> 12-bit ADC codes (host) ---------------------------------------------------------------------------
+extern "C" long sr_wav_to_adc12(const void *wav, size_t wav_bytes, uint16_t *out, size_t max_samples, uint32_t *sample_rate) {
+    const unsigned char *p = static_cast<const unsigned char *>(wav);
+    auto rd16 = [&](size_t o) { return (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8); };
+    auto rd32 = [&](size_t o) { return rd16(o) | (rd16(o + 2) << 16); };
+    if (!p || wav_bytes < 12 || memcmp(p, "RIFF", 4) != 0 || memcmp(p + 8, "WAVE", 4) != 0) return -1;
+    uint32_t fmt = 0, ch = 0, rate = 0, bits = 0;
+    size_t pos = 12, data_off = 0, data_len = 0;
+    while (pos + 8 <= wav_bytes) {
+        const uint32_t len = rd32(pos + 4);
+        if (memcmp(p + pos, "fmt ", 4) == 0 && pos + 8 + 16 <= wav_bytes) {
+            fmt = rd16(pos + 8); ch = rd16(pos + 10); rate = rd32(pos + 12); bits = rd16(pos + 22);
+        } else if (memcmp(p + pos, "data", 4) == 0) {
+            data_off = pos + 8;
+            data_len = len;
+            if (data_off + data_len > wav_bytes) data_len = wav_bytes - data_off;
+            break;
+        }
+        pos += 8 + (size_t)len + (len & 1);
+    }
+    if (fmt != 1 || ch == 0 || (bits != 8 && bits != 16) || data_off == 0) return -1;
+    if (sample_rate) *sample_rate = rate;
+    const size_t frame = (size_t)ch * (bits / 8), n = data_len / frame;
+    size_t k = 0;
+    for (; k < n && k < max_samples; ++k) {
+        const unsigned char *q = p + data_off + k * frame;
+        int v;
+        if (bits == 16) v = (int)(int16_t)(q[0] | (q[1] << 8)) / 16 + 2048;
+        else v = ((int)q[0] - 128) * 16 + 2048;
+        out[k] = (uint16_t)(v < 0 ? 0 : (v > 4095 ? 4095 : v));
+    }
+    return (long)k;
+}

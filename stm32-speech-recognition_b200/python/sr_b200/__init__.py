@@ -89,6 +89,8 @@ def lib():
         L.sr_synth_pcm_host.argtypes = [vp, u32, u32, u64, u32]
         L.sr_synth_pcm_dev.argtypes = [vp, u32, u32, u64, u32, vp]
         L.sr_synth_ftr_host.argtypes = [vp, u32, u32, u64, u32, u32]
+        L.sr_wav_to_adc12.argtypes = [vp, C.c_size_t, vp, C.c_size_t, vp]
+        L.sr_wav_to_adc12.restype = C.c_long
         L.noise_atap.argtypes = [vp, C.c_uint16, vp]
         L.noise_atap.restype = None
         L.VAD.argtypes = [vp, C.c_uint16, vp, vp]
@@ -334,6 +336,17 @@ def synth_ftr_host(B, seed_base, fmin=50, fmax=100, stride=FTR_BYTES):
     if rc != 0:
         raise SrError("sr_synth_ftr_host failed")
     return buf
+
+
+def wav_to_adc12(wav_bytes, max_samples=1 << 24):
+    """(samples u16[n], sample_rate) from the bytes of a RIFF/WAVE PCM file (include/sr_synth.h)"""
+    buf = np.frombuffer(wav_bytes, np.uint8).copy()
+    out = np.zeros(min(max_samples, max(len(buf), 1)), np.uint16)
+    rate = C.c_uint32(0)
+    n = lib().sr_wav_to_adc12(_p(buf), len(buf), _p(out), len(out), C.byref(rate))
+    if n < 0:
+        raise SrError("not a supported PCM WAV file")
+    return out[:n].copy(), rate.value
 
 
 def make_bank(ftr, slot_stride=4096, valid=None):

@@ -67,3 +67,32 @@ def test_host_synth_is_deterministic_and_in_range():
     # calibration window is noise only: |x - mid| <= 60
     mid = np.median(a[:, :2400], axis=1)
     assert (np.abs(a[:, :2400].astype(np.int64) - mid[:, None]) <= 61).all()
+
+
+def test_wav_ingestion_matches_the_documented_mapping(tmp_path):
+    """8/16-bit PCM WAV -> 12-bit unsigned ADC codes (x/16 + 2048), checked against python's wave module; and on the
+    reference's own recordings when the tree is mounted (the oracle then finds speech in them)"""
+    import io
+    import wave
+    rng = np.random.default_rng(0)
+    for width, nch in ((2, 1), (1, 1), (2, 2)):
+        n = 3000
+        x = rng.integers(-32768, 32768, (n, nch)).astype(np.int16) if width == 2 else rng.integers(0, 256, (n, nch)).astype(np.uint8)
+        bio = io.BytesIO()
+        with wave.open(bio, "wb") as w:
+            w.setnchannels(nch); w.setsampwidth(width); w.setframerate(8000); w.writeframes(x.tobytes())
+        got, rate = sr_b200.wav_to_adc12(bio.getvalue())
+        c0 = x[:, 0].astype(np.int64)
+        want = np.trunc(c0 / 16).astype(np.int64) + 2048 if width == 2 else (c0 - 128) * 16 + 2048
+        assert rate == 8000 and np.array_equal(got.astype(np.int64), np.clip(want, 0, 4095))
+    with pytest.raises(sr_b200.SrError):
+        sr_b200.wav_to_adc12(b"RIFFxxxxWAVEjunk")
+    ref_wav = "/root/reference/Matlab/\u8bed\u97f3\u6837\u672c/\u4e0a\u4e0b\u524d\u540e\u5de6\u53f3.wav"
+    if os.path.exists(ref_wav):
+        import oracle_bind as ob
+        pcm, rate = sr_b200.wav_to_adc12(open(ref_wav, "rb").read())
+        assert rate == 8000 and len(pcm) > 8000
+        o = ob.best_oracle()
+        atap = o.noise_atap(pcm[:16000].copy(), 2400)
+        seg = o.vad(pcm[:16000].copy(), min(len(pcm), 16000), atap)
+        assert seg[0] != ob.NULL                       # the reference's VAD opens a segment on its own recording
