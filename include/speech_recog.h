@@ -147,6 +147,12 @@ typedef struct {
 int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
                        const sr_recog_out *out);
 
+/* The same call spread over several GPUs of one box: contiguous shards, one host thread per handle, results
+ * written straight into the caller's host arrays (no collective needed for host outputs). handles[g] must be
+ * handles on different devices with the same bank set. */
+int sr_recognise_batch_multi(sr_handle *const *handles, uint32_t n_handles, const uint16_t *pcm, uint32_t U, uint32_t B,
+                             uint32_t n_len, const sr_recog_out *out);
+
 /* device-pointer variants: every pointer is device memory on the handle's device, calls are
  * asynchronous on the handle's stream. Alignment: pcm 2 bytes, everything else 4 bytes. */
 int sr_noise_atap_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, atap_tag *atap);

@@ -444,6 +444,37 @@ int sr_get_mdl_batch(sr_handle *h, const v_ftr_tag *in1, const v_ftr_tag *in2, u
     return 0;
 }
 
+// One host call, several GPUs: the batch is cut into contiguous shards, shard g runs on handles[g]
+// from its own host thread, and every shard writes its results straight into its slice of the caller's host
+// arrays -- with host outputs the "gather" is the D2H copies themselves, no collective is needed. (Device-resident
+// multi-GPU use is one process per GPU with a NCCL all-gather of the score blocks, see bench.py.)
+// All handles must have the same template bank set. Returns the first non-zero shard status.
+int sr_recognise_batch_multi(sr_handle *const *handles, uint32_t n_handles, const uint16_t *pcm, uint32_t U, uint32_t B,
+                             uint32_t n_len, const sr_recog_out *o) {
+    if (!handles || n_handles == 0 || !o) return fail(nullptr, "sr_recognise_batch_multi: bad arguments", cudaSuccess);
+    for (uint32_t g = 0; g < n_handles; ++g)
+        if (!handles[g] || handles[g]->n_slot != handles[0]->n_slot) return fail(nullptr, "sr_recognise_batch_multi: handles differ", cudaSuccess);
+    const size_t T = handles[0]->n_slot;
+    std::vector<int> rc(n_handles, 0);
+    std::vector<std::thread> th;
+    for (uint32_t g = 0; g < n_handles; ++g) {
+        const uint32_t lo = (uint32_t)((uint64_t)B * g / n_handles), hi = (uint32_t)((uint64_t)B * (g + 1) / n_handles);
+        sr_recog_out s = *o;
+        if (s.atap) s.atap += lo;
+        if (s.seg_off) s.seg_off += (size_t)lo * 6;
+        if (s.ftr) s.ftr += lo;
+        if (s.score) s.score += (size_t)lo * T;
+        if (s.best_idx) s.best_idx += lo;
+        if (s.best_dis) s.best_dis += lo;
+        if (s.cmd) s.cmd += lo;
+        if (s.status) s.status += lo;
+        th.emplace_back([=, &rc]() { rc[g] = sr_recognise_batch(handles[g], pcm + (size_t)lo * U, U, hi - lo, n_len, &s); });
+    }
+    for (auto &t : th) t.join();
+    for (uint32_t g = 0; g < n_handles; ++g) if (rc[g]) return rc[g];
+    return 0;
+}
+
 int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t n, uint32_t *mag) {
     SR_REQUIRE(h, h && (n == 0 || (frames && mag)));
     SR_REQUIRE(h, len <= SR_FFT_POINT);                                   // MFCC.C:32-35

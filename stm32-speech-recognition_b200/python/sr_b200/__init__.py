@@ -83,6 +83,7 @@ def lib():
             getattr(L, name).argtypes = [vp, vp, u32, u32, i32, vp, vp, vp]
         for name in ("sr_recognise_batch", "sr_recognise_batch_dev"):
             getattr(L, name).argtypes = [vp, vp, u32, u32, u32, C.POINTER(RecogOut)]
+        L.sr_recognise_batch_multi.argtypes = [C.POINTER(vp), u32, vp, u32, u32, u32, C.POINTER(RecogOut)]
         L.sr_fft_mag_batch.argtypes = [vp, vp, u32, u32, vp]
         L.sr_fft_raw_batch.argtypes = [vp, vp, u32, vp]
         L.sr_get_dis_batch.argtypes = [vp, vp, vp, u32, vp]
@@ -279,6 +280,31 @@ class Handle:
         ro = RecogOut(*[_p(ptrs.get(k)) for k in
                         ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
         self._ck(lib().sr_recognise_batch_dev(self._h, _p(pcm_ptr), U, B, n_len, C.byref(ro)))
+
+
+def recognise_multi(handles, pcm, n_len=2400, want=("best_idx", "best_dis", "cmd", "status", "score", "seg_off")):
+    """sr_recognise_batch_multi: one host call over several handles (one per GPU); numpy in/out"""
+    B, U = pcm.shape
+    T = handles[0].n_slot
+    out = {}
+    if "seg_off" in want:
+        out["seg_off"] = np.zeros((B, 3, 2), np.uint32)
+    if "ftr" in want:
+        out["ftr"] = np.zeros(B, FTR_DTYPE)
+    if "score" in want:
+        out["score"] = np.zeros((B, T), np.uint32)
+    for k in ("best_idx", "best_dis", "cmd"):
+        if k in want:
+            out[k] = np.zeros(B, np.uint32)
+    if "status" in want:
+        out["status"] = np.zeros(B, np.uint8)
+    ro = RecogOut(*[(_p(out[k]) if k in out else None) for k in
+                    ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
+    arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+    rc = lib().sr_recognise_batch_multi(arr, len(handles), _p(pcm), U, B, n_len, C.byref(ro))
+    if rc != 0:
+        raise SrError("sr_recognise_batch_multi failed (%d): %s" % (rc, lib().sr_last_error(None).decode()))
+    return out
 
 
 class StreamPool:

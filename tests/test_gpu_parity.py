@@ -450,6 +450,28 @@ def test_streaming_equals_batch(handle, ora, chunk):
         assert e["cmd"] == e["best_idx"] // 4
 
 
+def test_recognise_multi_handle_sharding(ora):
+    """sr_recognise_batch_multi: contiguous shards over several handles (all visible GPUs, or two handles on one GPU)
+    == the single-handle result, bit for bit"""
+    import torch
+    ng = max(1, torch.cuda.device_count())
+    devs = list(range(ng)) if ng > 1 else [0, 0]
+    B, U, T = 1003, 8000, 9
+    pcm = sr_b200.synth_pcm_host(B, U, 0x3131)
+    hs = [sr_b200.Handle(d) for d in devs]
+    bank, _ = hs[0].enrol(sr_b200.synth_pcm_host(T, U, 0x7E3A0000), 2400)
+    for h in hs:
+        h.set_bank(bank, T, 4096)
+    multi = sr_b200.recognise_multi(hs, pcm, 2400)
+    single = hs[0].recognise(pcm, 2400)
+    for k in multi:
+        assert np.array_equal(multi[k], single[k]), k
+    ref = ora.recognise_batch(pcm[:64], 2400, bank, T, 4096)
+    assert np.array_equal(multi["score"][:64], ref["score"])
+    for h in hs:
+        h.close()
+
+
 def test_thin_c_host_links_reference_named_symbols():
     """host/spch_host.c = save_mdl + spch_recg transcribed against the reference's headers (include/compat) and linked
     straight against libspeech_b200.so: single-call path and batched path must agree"""
