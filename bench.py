@@ -364,7 +364,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="recognise", choices=["recognise", "mfcc", "dtw", "dtw_band", "stream"])
     ap.add_argument("--streams", type=int, default=8192)
+    ap.add_argument("--samples", type=int, default=8000, help="samples per utterance (8000 = BASELINE's 1 s; 16000 = the reference's native 2 s buffer)")
     args = ap.parse_args()
+    global U
+    U = args.samples
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -559,10 +562,10 @@ def main():
         "metric": "utterances/s", "value": total_utts / (ms_step * 1e-3), "unit": "utterances/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed-point (s16 FFT, u32 energies)", "data": "synthetic",
-        "config": {"workload": "configs[1]: 65536 x 1 s utterances (8 kHz u16), 12 MFCC, 20 templates, per GPU; "
+        "config": {"workload": "configs[1]: %d x %g s utterances (8 kHz u16), 12 MFCC, %d templates, per GPU; " % (B, U / 8000.0, T) +
                                "full spch_recg path: noise_atap+VAD -> get_mfcc(seg 0) -> dtw x T -> argmin",
                    "utterances_per_gpu": B, "samples_per_utterance": U, "templates": T, "geometry": "160/80/1024 (reference)",
-                   "l2": "inputs (1.05 GB PCM per GPU) exceed the 126 MB L2; no flush needed",
+                   "l2": "inputs (%.2f GB PCM per GPU) exceed the 126 MB L2; no flush needed" % (B * U * 2 / 1e9),
                    "multi_gpu": "utterances sharded, one NCCL all_gather of u32 scores [B,T] per step" if world > 1 else "single GPU"},
         "mfcc_frames_per_s": frames_total / (ms_step * 1e-3),
         "vad_ok_fraction": ok_total / total_utts,
