@@ -40,12 +40,35 @@ __device__ __forceinline__ u32 warp_max(u32 v) {
 // per-block summary: bs = sum |x-mid| over the 80 samples; flags = zc (bits 0..6, alternations inside the
 // block) | lc << 7 (class of last out-of-band sample, 0 none / 1 below / 2 above) | lcA << 9 (same over the
 // first 79 samples) | p0 << 11 (sample 0 is out of band)
+// Word-level alternation count. H / L = bitmaps (bit i = sample i) of the samples above / below the band
+// (disjoint), `last` = class (0 none / 1 below / 2 above) of the last out-of-band sample before bit 0 of this
+// word -- 0 means "unknown" and never counts (the frame-level pass applies the carried-in state separately).
+// Returns the number of out-of-band samples whose class differs from the previous out-of-band sample's and
+// updates `last`. The previous class of every position comes from a segmented forward fill of H over the
+// markers N = H|L (5 doubling steps) instead of a per-sample state machine.
+__device__ __forceinline__ u32 word_alternations(u32 H, u32 L, u32 &last) {
+    const u32 N = H | L;
+    u32 P = H, K = ~N;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { P |= K & (P << d); K &= K << d; }
+    // P[i]: the most recent marker at or before i is "above"
+    const u32 low = N & (0u - N);                       // lowest marker
+    const u32 seen = ~(low | (low - 1u));               // positions strictly above the lowest marker (0 if N == 0)
+    const u32 in2 = last == 2u ? 0xFFFFFFFFu : 0u, in1 = last == 1u ? 0xFFFFFFFFu : 0u;
+    const u32 prevH = ((P << 1) & seen) | (~seen & in2);
+    const u32 prevL = (~(P << 1) & seen) | (~seen & in1);
+    const u32 alt = (H & prevL) | (L & prevH);
+    if (N) last = ((H >> (31 - __clz(N))) & 1u) ? 2u : 1u;
+    return __popc(alt);
+}
+
+// Per-block summary, built from bitmaps: per sample only 1 extract + 1 VABSDIFF + 2 compares + 2 predicated ORs.
 __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid, u32 a_thl, u32 b_thl, u32 &bs_out,
                                            u32 &flags_out) {
-    u32 bs = 0, zc = 0, lcA = 0;
-    bool lastHi = false, lastLo = false, p0 = false;
+    u32 bs = 0;
+    u32 H[3] = {0, 0, 0}, L[3] = {0, 0, 0};            // samples 0..31, 32..63, 64..79
     const u16 *p = v.x + i0;
-#pragma unroll 2
+#pragma unroll
     for (int c = 0; c < 10; ++c) {
         u32 w[4];
         if (v.vec_ok) {
@@ -57,20 +80,29 @@ __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            const int h = 8 * c + j;
             const u32 s = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu);
             bs = __usad(s, mid, bs);                                        // VAD.C:126-129
-            const bool hi = s >= a_thl;                                     // VAD.C:134-141: ">= a" first, else "< b"
-            const bool lo = !hi && s < b_thl;
-            zc += ((hi && lastLo) || (lo && lastHi)) ? 1u : 0u;             // VAD.C:143-156
-            lastHi = hi || (lastHi && !lo);
-            lastLo = lo || (lastLo && !hi);
-            if (c == 0 && j == 0) p0 = hi || lo;
-            if (c == 9 && j == 6) lcA = lastHi ? 2u : (lastLo ? 1u : 0u);   // after sample 78
+            if (s >= a_thl) H[h >> 5] |= 1u << (h & 31);                    // VAD.C:134-141 / 143-156
+            if (s < b_thl) L[h >> 5] |= 1u << (h & 31);
         }
     }
-    const u32 lc = lastHi ? 2u : (lastLo ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) L[k] &= ~H[k];                              // ">= a" is tested first, "< b" only else
+    u32 last = 0, zc = 0;
+    zc += word_alternations(H[0], L[0], last);
+    zc += word_alternations(H[1], L[1], last);
+    u32 lastA = last;                                                       // state after sample 63
+    const u32 zc2 = word_alternations(H[2], L[2], last);
+    zc += zc2;
+    // last class among the first 79 samples: redo the (cheap) "last" update of word 2 without sample 79 (bit 15)
+    {
+        const u32 Hm = H[2] & 0x7FFFu, Nm = (H[2] | L[2]) & 0x7FFFu;
+        if (Nm) lastA = ((Hm >> (31 - __clz(Nm))) & 1u) ? 2u : 1u;
+    }
+    const u32 p0 = (H[0] | L[0]) & 1u;
     bs_out = bs;
-    flags_out = zc | (lc << 7) | (lcA << 9) | ((p0 ? 1u : 0u) << 11);
+    flags_out = zc | (last << 7) | (lastA << 9) | (p0 << 11);
 }
 
 // position of the first set bit at index >= from in a bitmap held one 32-bit word per lane; -1 if none
