@@ -185,6 +185,61 @@ def test_vad_lengths(handle, ora, U, buf_len):
             assert (seg[b] == ob.NULL).all()
 
 
+def test_vad_and_mfcc_fuzz_with_arbitrary_atap(handle, ora):
+    """random PCM shapes and ARBITRARY adaptive parameters handed straight to VAD / get_mfcc (n_thl > mid makes the lower
+    band edge wrap, VAD.C:113; huge mid_val exercises the s32 casts of MFCC.C:110,119)"""
+    rng = np.random.default_rng(77)
+    B, U = 256, 4000
+    pcm = np.zeros((B, U), np.uint16)
+    for b in range(B):
+        kind = b % 6
+        base = int(rng.integers(0, 4096))
+        if kind == 0:
+            pcm[b] = rng.integers(0, 4096, U)
+        elif kind == 1:
+            pcm[b] = np.clip(base + rng.integers(-30, 31, U), 0, 65535)
+            idx = rng.integers(0, U, 200)
+            pcm[b, idx] = rng.integers(0, 4096, 200)
+        elif kind == 2:
+            t = np.arange(U)
+            pcm[b] = np.clip(2048 + 1500 * np.sin(t * rng.uniform(0.01, 1.5)) * (rng.random(U) < 0.7), 0, 4095)
+        elif kind == 3:
+            pcm[b] = rng.integers(0, 65536, U)
+        elif kind == 4:
+            pcm[b] = np.where(rng.random(U) < 0.05, rng.integers(0, 4096, U), base)
+        else:
+            blocks = rng.integers(0, 2, U // 80 + 1).repeat(80)[:U]
+            pcm[b] = np.where(blocks == 1, rng.integers(0, 4096, U), base)
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = rng.integers(0, 4096, B)
+    atap["n_thl"] = rng.integers(0, 3000, B)          # often > mid_val: b_thl wraps
+    atap["z_thl"] = rng.integers(0, 12, B)
+    atap["s_thl"] = rng.integers(0, 200000, B)
+    atap["mid_val"][:8] = rng.integers(60000, 2 ** 32, 8, dtype=np.uint64).astype(np.uint32)
+    seg = handle.vad(pcm, atap)
+    for b in range(B):
+        assert ora.vad(pcm[b], U, atap[b:b + 1]).tolist() == seg[b].reshape(-1).tolist(), b
+    st = rng.integers(1, 2000, B)
+    en = np.minimum(st + rng.integers(160, 1800, B), U)
+    sg = np.stack([st, en], 1).astype(np.uint32)
+    assert ob.ftr_equal(handle.mfcc(pcm, sg, atap), ora.mfcc_batch(pcm, sg, atap))
+
+
+def test_dtw_fuzz_many_pairs(handle, ora):
+    """20 000 random pairs over all length combinations, realistic and adversarial value ranges, T not a multiple of 32"""
+    rng = np.random.default_rng(78)
+    B, T = 400, 50
+    ftr = sr_b200.synth_ftr_host(B, 0xF00D, 1, 119).view(sr_b200.FTR_DTYPE).reshape(-1).copy()
+    ftr["mfcc_dat"][::3] = rng.integers(-32768, 32768, ftr["mfcc_dat"][::3].shape)      # every third: full-range values
+    ftr["mfcc_dat"][1::7] //= 64                                                          # small values: many equal distances (ties)
+    bank = sr_b200.synth_ftr_host(T, 0xFEED, 1, 119, stride=2860)
+    bank[::5, 4:] = rng.integers(0, 256, bank[::5, 4:].shape)
+    handle.set_bank(bank, T, 2860)
+    want, _ = ora.dtw_batch(ftr, bank, T, 2860)
+    score, bi, bd = handle.dtw(ftr)
+    assert np.array_equal(score, want)
+
+
 # ---- dtw ---------------------------------------------------------------------------------------------
 def test_dtw_all_lengths_bit_exact(handle, ora):
     B, T = 150, 70
