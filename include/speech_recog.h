@@ -11,6 +11,7 @@
  *          dtw          Src/Speech_Recog/DTW.H:7    (DTW.C:120-192)
  *          fft          Src/Speech_Recog/MFCC.C:27  (global, no header)
  *          get_dis      Src/Speech_Recog/DTW.C:45   (global, no header)
+ *          dtw_limit    Src/Speech_Recog/DTW.C:76   (global, no header; its file-static state is per thread here)
  *      A host program written against VAD.H / MFCC.H / DTW.H links unchanged (see include/compat/).
  *
  *  (2) Batched, re-entrant forms on an explicit handle (sr_*): B independent utterances per call,
@@ -89,6 +90,7 @@ void      get_mfcc(valid_tag *valid, v_ftr_tag *v_ftr, atap_tag *atap_arg);
 uint32_t  dtw(v_ftr_tag *ftr_in, v_ftr_tag *frt_mdl);
 uint32_t *fft(int16_t *dat_buf, uint16_t buf_len);        /* returns a thread-local u32[1024]; [0,512) valid */
 uint32_t  get_dis(int16_t *frm_ftr1, int16_t *frm_ftr2);
+uint8_t   dtw_limit(uint16_t x, uint16_t y);            /* DTW.C:76: 0 ins / 1 outs, for the (I,M) of this thread's last dtw() */
 
 /* ---- (2) batched handle API -----------------------------------------------------------------
  * A handle owns its device workspaces and stream; use one handle per thread (calls on the same handle must not
@@ -200,6 +202,9 @@ int sr_streams_segments(sr_stream_pool *p, uint32_t *seg_off /* [n_streams][3][2
  * `len` (<=1024) s16 samples each -> u32[n][512]; get_dis (DTW.C:45-62) of n row pairs. */
 int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t n, uint32_t *mag);
 int sr_get_dis_batch(sr_handle *h, const int16_t *a, const int16_t *b, uint32_t n, uint32_t *dis);
+/* dtw_limit (DTW.C:76-109) for n points with explicit frame counts: out[i] = 0 ins / 1 outs */
+int sr_dtw_limit_batch(sr_handle *h, const uint16_t *x, const uint16_t *y, const uint16_t *I, const uint16_t *M, uint32_t n,
+                       uint8_t *out);
 /* raw cr4_fft_1024_stm32 (Src/BSP/cr4_fft_1024_stm32.s:219-281) of n packed inputs (re | im<<16,
  * u32[n][1024]) -> packed outputs; exists so tests can pin the FFT kernel code against the asm restatement
  * on arbitrary complex data */

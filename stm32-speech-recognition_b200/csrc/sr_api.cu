@@ -490,6 +490,23 @@ int sr_fft_mag_batch(sr_handle *h, const int16_t *frames, uint32_t len, uint32_t
     return 0;
 }
 
+// dtw_limit (DTW.C:76-109) for n points, explicit (I, M) per point instead of the reference's file statics
+int sr_dtw_limit_batch(sr_handle *h, const uint16_t *x, const uint16_t *y, const uint16_t *I, const uint16_t *M, uint32_t n,
+                       uint8_t *out) {
+    SR_REQUIRE(h, h && (n == 0 || (x && y && I && M && out)));
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->misc0, (size_t)n * 8 + 16));
+    SR_CK(h, ensure(h->misc2, (size_t)n + 16));
+    u16 *d = static_cast<u16 *>(h->misc0.p);
+    H2D(h, d, x, (size_t)n * 2); H2D(h, d + n, y, (size_t)n * 2); H2D(h, d + 2 * (size_t)n, I, (size_t)n * 2); H2D(h, d + 3 * (size_t)n, M, (size_t)n * 2);
+    SR_CK(h, launch_dtw_limit(d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, n, static_cast<u8 *>(h->misc2.p), h->stream));
+    ++h->launches;
+    D2H(h, out, h->misc2.p, (size_t)n);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // raw FFT of packed (re | im<<16) 1024-point inputs -- test hook for the asm restatement parity
 int sr_fft_raw_batch(sr_handle *h, const uint32_t *in_packed, uint32_t n, uint32_t *out_packed) {
     SR_REQUIRE(h, h && (n == 0 || (in_packed && out_packed)));
@@ -583,11 +600,26 @@ void get_mfcc(valid_tag *valid, v_ftr_tag *v_ftr, atap_tag *atap_arg) {
     if (sr_mfcc_batch(h, valid->start - 1, U, 1, seg, 2, atap_arg, v_ftr) != 0) v_ftr->frm_num = 0;
 }
 
+// the reference keeps in_frm_num / mdl_frm_num of the last dtw() call in file statics (DTW.C:65-68, set at :130-131);
+// dtw_limit() reads them. Here they are per calling thread.
+static thread_local uint16_t g_last_I = 0, g_last_M = 0;
+
+// DTW.C:76-109 (global, no header): 0 = "ins", 1 = "outs", for the (I, M) of this thread's last dtw() call
+uint8_t dtw_limit(uint16_t x, uint16_t y) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    sr_handle *h = default_handle();
+    uint8_t r = 1;
+    if (!h) return r;
+    if (sr_dtw_limit_batch(h, &x, &y, &g_last_I, &g_last_M, 1, &r) != 0) return 1;
+    return r;
+}
+
 // DTW.H:7 / DTW.C:120-192
 uint32_t dtw(v_ftr_tag *ftr_in, v_ftr_tag *frt_mdl) {
     std::lock_guard<std::mutex> lk(g_default_mu);
     sr_handle *h = default_handle();
     if (!h || !ftr_in || !frt_mdl) return SR_DIS_ERR;
+    g_last_I = ftr_in->frm_num; g_last_M = frt_mdl->frm_num;                  // DTW.C:130-131
     const void *sv_bank = h->bank; const u32 sv_n = h->n_slot, sv_s = h->slot_stride;
     uint32_t score = SR_DIS_ERR;
     DeviceGuard g(h->device);

@@ -290,6 +290,20 @@ cudaError_t launch_pack_slots(const void *ftr, const u8 *status, u32 B, void *ba
     return cudaGetLastError();
 }
 
+// dtw_limit (DTW.C:76-109) for n points: out[i] = 0 "ins" / 1 "outs" for (x[i], y[i]) in the parallelogram of (I[i], M[i])
+__global__ void dtw_limit_kernel(const u16 *x, const u16 *y, const u16 *I, const u16 *M, u32 n, u8 *out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Ii = I[i], Mi = M[i];
+    const int X1 = (int)(u16)((2 * Mi - Ii) / 3), X2 = (int)(u16)((4 * Ii - 2 * Mi) / 3);   // u16 statics, DTW.C:65-66,141-142
+    out[i] = ins_xy(x[i], y[i], X1, X2, Ii, Mi) ? 0 : 1;
+}
+cudaError_t launch_dtw_limit(const u16 *x, const u16 *y, const u16 *I, const u16 *M, u32 n, u8 *out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    dtw_limit_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, y, I, M, n, out);
+    return cudaGetLastError();
+}
+
 // get_dis for n independent row pairs (secondary drop-in symbol, DTW.C:45-62)
 __global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -87,6 +87,9 @@ def lib():
         L.sr_fft_mag_batch.argtypes = [vp, vp, u32, u32, vp]
         L.sr_fft_raw_batch.argtypes = [vp, vp, u32, vp]
         L.sr_get_dis_batch.argtypes = [vp, vp, vp, u32, vp]
+        L.sr_dtw_limit_batch.argtypes = [vp, vp, vp, vp, vp, u32, vp]
+        L.dtw_limit.argtypes = [C.c_uint16, C.c_uint16]
+        L.dtw_limit.restype = C.c_uint8
         L.sr_synth_pcm_host.argtypes = [vp, u32, u32, u64, u32]
         L.sr_synth_pcm_dev.argtypes = [vp, u32, u32, u64, u32, vp]
         L.sr_synth_ftr_host.argtypes = [vp, u32, u32, u64, u32, u32]

@@ -225,6 +225,29 @@ def test_vad_and_mfcc_fuzz_with_arbitrary_atap(handle, ora):
     assert ob.ftr_equal(handle.mfcc(pcm, sg, atap), ora.mfcc_batch(pcm, sg, atap))
 
 
+def test_dtw_limit_batch_and_drop_in_symbol(handle, ora):
+    """dtw_limit (DTW.C:76-109): every lattice point of a few (I, M) shapes, and the reference-named symbol after dtw()"""
+    L = sr_b200.lib()
+    pts = []
+    for (I, M) in ((36, 34), (50, 100), (100, 50), (119, 60), (1, 1), (8, 15)):
+        for x in range(0, I + 3):
+            for y in range(0, M + 3):
+                pts.append((x, y, I, M))
+    a = np.array(pts, np.uint16)
+    out = np.zeros(len(pts), np.uint8)
+    cols = [np.ascontiguousarray(a[:, k]) for k in range(4)]
+    rc = L.sr_dtw_limit_batch(handle._h, *[c.ctypes.data_as(C.c_void_p) for c in cols], len(pts), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    po = ob.port()
+    want = np.array([po.lib.sro_dtw_limit(int(x), int(y), int(I), int(M)) for x, y, I, M in pts], np.uint8)
+    assert np.array_equal(out, want) and 0 < want.sum() < len(pts)
+    f = sr_b200.synth_ftr_host(2, 0xABC, 30, 40).view(sr_b200.FTR_DTYPE).reshape(-1)
+    L.dtw(f[0:1].ctypes.data_as(C.c_void_p), f[1:2].ctypes.data_as(C.c_void_p))
+    I, M = int(f["frm_num"][0]), int(f["frm_num"][1])
+    for x, y in ((1, 1), (5, 20), (20, 5), (I, M), (2, 9)):
+        assert L.dtw_limit(x, y) == po.lib.sro_dtw_limit(x, y, I, M)
+
+
 def test_dtw_fuzz_many_pairs(handle, ora):
     """20 000 random pairs over all length combinations, realistic and adversarial value ranges, T not a multiple of 32"""
     rng = np.random.default_rng(78)
