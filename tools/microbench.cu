@@ -39,6 +39,9 @@ __global__ void k(uint32_t *out, uint32_t a0, uint32_t b0, long long *cyc) {
             if (OP == 13) { acc[i] = acc[i] * b + 12345u; facc[i] = facc[i] * 1.0001f + 0.5f; } // IMAD + FFMA mix
             if (OP == 14) { acc[i] = acc[i] * b + 12345u; asm volatile("shr.s32 %0, %0, 1;" : "+r"(acc[(i + 4) & 7])); } // IMAD + SHF mix
             if (OP == 15) asm volatile("vabsdiff.u32.u32.u32.add %0, %0, %1, %0;" : "+r"(acc[i]) : "r"(b));
+            if (OP == 16) { unsigned long long w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(acc[i]), "r"(b)); acc[i] = (uint32_t)(w >> 32) + (uint32_t)w; }  // IMAD.WIDE.U32 + IADD
+            if (OP == 17) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(b));                  // IMAD.HI.U32
+            if (OP == 18) { unsigned long long w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(acc[i]), "r"(b)); acc[i] = (uint32_t)(w >> 37); }   // udiv-by-constant via WIDE + SHF
         }
     }
     long long t1 = clock64();
@@ -68,5 +71,6 @@ int main() {
     run<5>("IDP.4A (dp4a)", 1); run<12>("IDP.2A (dp2a)", 1); run<6>("IMAD.HI", 1); run<7>("a>>16 + b (LEA.HI?)", 1);
     run<8>("FFMA", 1); run<9>("MUFU.RSQ", 1); run<10>("I2F + LOP", 2); run<11>("usad", 1); run<15>("vabsdiff.add", 1);
     run<13>("IMAD + FFMA", 2); run<14>("IMAD + SHF", 2);
+    run<16>("IMAD.WIDE.U32 + IADD", 2); run<17>("IMAD.HI.U32 (mul.hi)", 1); run<18>("IMAD.WIDE.U32 + SHF", 2);
     return 0;
 }
