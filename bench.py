@@ -568,6 +568,7 @@ def main():
                    "l2": "inputs (%.2f GB PCM per GPU) exceed the 126 MB L2; no flush needed" % (B * U * 2 / 1e9),
                    "multi_gpu": "utterances sharded, one NCCL all_gather of u32 scores [B,T] per step" if world > 1 else "single GPU"},
         "mfcc_frames_per_s": frames_total / (ms_step * 1e-3),
+        "dtw_pairs_per_s": ok_total * T / (ms_step * 1e-3),      # greedy walks per second (cells/s: bench.py --workload dtw)
         "vad_ok_fraction": ok_total / total_utts,
         "kernel_ms": kern_ms, "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu_sample": parity,
         "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utterances/s", "ms_per_step": e2e_ms,
