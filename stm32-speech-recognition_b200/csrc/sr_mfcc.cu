@@ -6,7 +6,7 @@
 //     utterance's PCM segment [start-1, end) into a 3-deep shared-memory ring with 1-D bulk
 //     async copies (TMA engine, cp.async.bulk + mbarrier complete_tx), so every PCM sample is
 //     read from HBM exactly once although frames overlap by 50 %;
-//   * 16 CONSUMER warps take frames round-robin from the CTA's concatenated frame stream,
+//   * 15 CONSUMER warps (see the variant table below) take frames round-robin from the CTA's concatenated frame stream,
 //     one frame per warp: pre-emphasis + Hamming (MFCC.C:115-124), FFT, |.| (MFCC.C:49-60),
 //     energy (MFCC.C:128-133), 24 triangular filters (MFCC.C:136-162), log (MFCC.C:165-170),
 //     DCT (MFCC.C:173-183) -> 12 x s16.
