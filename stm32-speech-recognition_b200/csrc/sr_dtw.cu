@@ -16,6 +16,7 @@
 namespace srk {
 
 constexpr int kDtwWarps = 16;
+constexpr int kK2Warps = 32;                // dtw_kernel: 1024 threads x 64 registers, more walks in flight per SM
 constexpr int kTileT = 32;
 
 // ---- byte-plane rows: 6 words = lo bytes of dims 0..11 (3 words) then hi bytes (3 words) -----------------
@@ -73,22 +74,22 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
     else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(kDtwWarps * 32)
+__global__ void __launch_bounds__(kK2Warps * 32)
 dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
            u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best,
            const u8 *__restrict__ status /* may be NULL: per-utterance SR_ST_* gate of sr_recognise */,
-           int Wg, int NU, int G, u32 tile0) {
+           int Wg, int NU, int G, u32 tile0, int tslots /* template slots allocated in shared memory */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 t0 = (blockIdx.x + tile0) * kTileT;
     const int Tt = (int)min((u32)kTileT, T - t0);
     unsigned char *tile = smem_raw;                                   // Tt slots
-    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)kTileT * kSlotBytes);   // [32]
-    unsigned char *uslots = smem_raw + (size_t)kTileT * kSlotBytes + 128;          // G*NU slots
+    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)tslots * kSlotBytes);   // [32]
+    unsigned char *uslots = smem_raw + (size_t)tslots * kSlotBytes + 128;          // G*NU slots
     u32 *ufrm = reinterpret_cast<u32 *>(uslots + (size_t)G * NU * kSlotBytes);     // [G*NU]
 
     // ---- template tile: byte-plane rows + norms + frame counts ----------------------------------------
-    for (int tt = warp; tt < Tt; tt += kDtwWarps) {
+    for (int tt = warp; tt < Tt; tt += kK2Warps) {
         const unsigned char *slot = bank + (size_t)(t0 + tt) * slot_stride;
         const u32 hdr = *reinterpret_cast<const u32 *>(slot);
         u32 frm = hdr >> 16;
@@ -321,20 +322,21 @@ static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank,
                                     u32 *score, u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 tile0,
                                     u32 ntiles, int Tt) {
     // lane packing: groups of Wg warps walk NU utterances x Tt templates; pick the best (Wg, NU, G)
-    const size_t budget = 224 * 1024 - (size_t)kTileT * kSlotBytes - 128 - 256;
+    const size_t budget = 224 * 1024 - (size_t)Tt * kSlotBytes - 128 - 512;
     const int slots_max = (int)(budget / kSlotBytes);
-    int bestWg = 1, bestNU = 1, bestG = kDtwWarps;
+    int bestWg = 1, bestNU = 1, bestG = 1;
     double best_util = -1.0;
-    for (int Wg = 1; Wg <= 8; ++Wg) {                       // named barriers 1..8
+    for (int Wg = 1; Wg <= 8; ++Wg) {
         const int NU = (32 * Wg) / Tt;
         if (NU < 1) continue;
-        int G = kDtwWarps / Wg;
+        int G = kK2Warps / Wg;
         if (G > slots_max / NU) G = slots_max / NU;
+        if (Wg > 1 && G > 15) G = 15;                       // named barriers 1..15
         if (G < 1) continue;
-        const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kDtwWarps);
+        const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kK2Warps);
         if (util > best_util + 1e-9) { best_util = util; bestWg = Wg; bestNU = NU; bestG = G; }
     }
-    const size_t smem = (size_t)kTileT * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
+    const size_t smem = (size_t)Tt * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
     cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     u32 gy = ((u32)num_sms + ntiles - 1) / ntiles;
@@ -343,9 +345,9 @@ static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank,
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
     dim3 grid(ntiles, gy);
-    dtw_kernel<<<grid, kDtwWarps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
-                                                  static_cast<const unsigned char *>(bank), T, slot_stride, flags,
-                                                  score, best, status, bestWg, bestNU, bestG, tile0);
+    dtw_kernel<<<grid, kK2Warps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
+                                                 static_cast<const unsigned char *>(bank), T, slot_stride, flags,
+                                                 score, best, status, bestWg, bestNU, bestG, tile0, Tt);
     return cudaGetLastError();
 }
 
