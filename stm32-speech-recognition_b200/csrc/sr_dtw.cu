@@ -339,7 +339,7 @@ static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank,
     const size_t smem = (size_t)Tt * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
     cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
-    u32 gy = ((u32)num_sms + ntiles - 1) / ntiles;
+    u32 gy = (u32)num_sms / ntiles;                      // floor: one CTA per SM, never a second partial wave
     const u32 ugroups = (B + (u32)(bestG * bestNU) - 1) / (u32)(bestG * bestNU);
     if (gy > ugroups) gy = ugroups;
     if (gy < 1) gy = 1;
@@ -482,20 +482,20 @@ dtw_band_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned 
 // c_i = floor(i*M/I); it slides by s = c_i - c_{i-1} in {0,1,2} per row, realised as two predicated shift-by-one
 // passes over the register array (no divergence between lanes whose templates have different lengths).
 template <int R>
-__global__ void __launch_bounds__(kDtwWarps * 32)
+__global__ void __launch_bounds__(kK2Warps * 32)
 dtw_band_thread_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
                        u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best, int Wg, int NU, int G,
-                       u32 tile0) {
+                       u32 tile0, int tslots) {
     constexpr int W = 2 * R + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 t0 = (blockIdx.x + tile0) * kTileT;
     const int Tt = (int)min((u32)kTileT, T - t0);
     unsigned char *tile = smem_raw;
-    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)kTileT * kSlotBytes);
-    unsigned char *uslots = smem_raw + (size_t)kTileT * kSlotBytes + 128;
+    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)tslots * kSlotBytes);
+    unsigned char *uslots = smem_raw + (size_t)tslots * kSlotBytes + 128;
     u32 *ufrm = reinterpret_cast<u32 *>(uslots + (size_t)G * NU * kSlotBytes);
-    for (int tt = warp; tt < Tt; tt += kDtwWarps) {
+    for (int tt = warp; tt < Tt; tt += kK2Warps) {
         const unsigned char *slot = bank + (size_t)(t0 + tt) * slot_stride;
         const u32 hdr = *reinterpret_cast<const u32 *>(slot);
         u32 frm = hdr >> 16;
@@ -591,31 +591,32 @@ dtw_band_thread_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const un
 
 static cudaError_t launch_band_thread_tiles(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags,
                                             u32 *score, u64 *best, int num_sms, cudaStream_t st, u32 tile0, u32 ntiles, int Tt) {
-    const size_t budget = 224 * 1024 - (size_t)kTileT * kSlotBytes - 128 - 256;
+    const size_t budget = 224 * 1024 - (size_t)Tt * kSlotBytes - 128 - 512;
     const int slots_max = (int)(budget / kSlotBytes);
-    int bestWg = 1, bestNU = 1, bestG = kDtwWarps;
+    int bestWg = 1, bestNU = 1, bestG = 1;
     double best_util = -1.0;
     for (int Wg = 1; Wg <= 8; ++Wg) {
         const int NU = (32 * Wg) / Tt;
         if (NU < 1) continue;
-        int G = kDtwWarps / Wg;
+        int G = kK2Warps / Wg;
         if (G > slots_max / NU) G = slots_max / NU;
+        if (Wg > 1 && G > 15) G = 15;
         if (G < 1) continue;
-        const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kDtwWarps);
+        const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kK2Warps);
         if (util > best_util + 1e-9) { best_util = util; bestWg = Wg; bestNU = NU; bestG = G; }
     }
-    const size_t smem = (size_t)kTileT * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
+    const size_t smem = (size_t)Tt * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
     cudaError_t e = cudaFuncSetAttribute(dtw_band_thread_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
-    u32 gy = ((u32)num_sms + ntiles - 1) / ntiles;
+    u32 gy = (u32)num_sms / ntiles;                      // floor: one CTA per SM, never a second partial wave
     const u32 ugroups = (B + (u32)(bestG * bestNU) - 1) / (u32)(bestG * bestNU);
     if (gy > ugroups) gy = ugroups;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
     dim3 grid(ntiles, gy);
-    dtw_band_thread_kernel<10><<<grid, kDtwWarps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
+    dtw_band_thread_kernel<10><<<grid, kK2Warps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
                                                                   static_cast<const unsigned char *>(bank), T, slot_stride,
-                                                                  flags, score, best, bestWg, bestNU, bestG, tile0);
+                                                                  flags, score, best, bestWg, bestNU, bestG, tile0, Tt);
     return cudaGetLastError();
 }
 
@@ -636,7 +637,7 @@ cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, 
     cudaError_t e = cudaFuncSetAttribute(dtw_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_smem);
     if (e != cudaSuccess) return e;
     const u32 tiles = (T + kTileT - 1) / kTileT;
-    u32 gy = ((u32)num_sms + tiles - 1) / tiles;
+    u32 gy = (u32)num_sms / tiles;                       // floor: never a second partial wave
     const u32 ugroups = (B + kDtwWarps - 1) / kDtwWarps;
     if (gy > ugroups) gy = ugroups;
     if (gy < 1) gy = 1;
