@@ -19,7 +19,7 @@
 
 namespace srk {
 
-constexpr int kVadMaxWarps = 12;
+constexpr int kVadMaxWarps = 32;
 
 struct VadWarpView {
     const u16 *x;       // staged samples, x[0] = first sample of the utterance
@@ -123,6 +123,43 @@ __device__ __forceinline__ u32 bm_shr(u32 x, int s, int lane) {
     return (x >> s) | (nxt << (32 - s));
 }
 
+// stage samples [first, first+count) of the batch into `buf` (bulk async copy when the batch base is 16-byte
+// aligned, plain loads otherwise); returns the sample index of `first` inside buf
+__device__ __forceinline__ int stage_chunk(unsigned char *buf, const u16 *pcm, size_t total_bytes, bool base_aligned,
+                                           size_t first, u32 count, u64 *bar, u32 &phase, int lane) {
+    if (count == 0) return 0;
+    const size_t lo = first * 2, hi = lo + (size_t)count * 2;
+    if (base_aligned) {
+        const size_t lo_al = lo & ~(size_t)15;
+        size_t hi_al = (hi + 15) & ~(size_t)15;
+        const size_t lim = total_bytes & ~(size_t)15;
+        if (hi_al > lim) hi_al = lim;
+        const int shift = (int)((lo - lo_al) >> 1);
+        if (hi > hi_al) {                                        // tail beyond the last whole 16-byte granule
+            const u16 *g = reinterpret_cast<const u16 *>(reinterpret_cast<const unsigned char *>(pcm) + hi_al);
+            u16 *d = reinterpret_cast<u16 *>(buf + (hi_al - lo_al));
+            const int n = (int)((hi - hi_al) >> 1);
+            if (lane < n) d[lane] = g[lane];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const u32 nbytes = (u32)(hi_al - lo_al);
+            mbar_arrive_expect_tx(bar, nbytes);
+            bulk_g2s(buf, reinterpret_cast<const unsigned char *>(pcm) + lo_al, nbytes, bar);
+        }
+        mbar_wait(bar, phase & 1u);
+        ++phase;
+        return shift;
+    }
+    const u16 *g = pcm + first;
+    u16 *d = reinterpret_cast<u16 *>(buf);
+    for (u32 i = lane; i < count; i += 32) d[i] = g[i];
+    __syncwarp();
+    return 0;
+}
+
+constexpr u32 kVadChunk = 32 * 80;                               // samples per staged chunk: one 80-sample block per lane
+
 __global__ void __launch_bounds__(kVadMaxWarps * 32)
 vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad,
            atap_tag *__restrict__ atap, u32 *__restrict__ seg_off, u32 buf_bytes, u32 max_frames) {
@@ -137,88 +174,80 @@ vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, in
 
     const size_t total_bytes = (size_t)B * U * 2;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
-    u32 need = 0;                                                  // samples this call touches per utterance
-    if (do_atap) need = n_len;
-    if (do_vad && buf_len > need) need = buf_len;
-    if (need > U) need = U;
+    u32 phase = 0;                                                 // completed bulk copies of this warp's barrier
 
-    int it = 0;
-    for (u32 b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps, ++it) {
-        // ---- stage samples [b*U, b*U+need) ----------------------------------------------------
-        const size_t lo = (size_t)b * U * 2, hi = lo + (size_t)need * 2;
-        int shift = 0;
-        if (base_aligned && need > 0) {
-            const size_t lo_al = lo & ~(size_t)15;
-            size_t hi_al = (hi + 15) & ~(size_t)15;
-            const size_t lim = total_bytes & ~(size_t)15;
-            if (hi_al > lim) hi_al = lim;
-            shift = (int)((lo - lo_al) >> 1);
-            if (hi > hi_al) {
-                const u16 *g = reinterpret_cast<const u16 *>(reinterpret_cast<const unsigned char *>(pcm) + hi_al);
-                u16 *d = reinterpret_cast<u16 *>(buf + (hi_al - lo_al));
-                const int n = (int)((hi - hi_al) >> 1);
-                if (lane < n) d[lane] = g[lane];
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const u32 nbytes = (u32)(hi_al - lo_al);
-                mbar_arrive_expect_tx(&bars[warp], nbytes);
-                bulk_g2s(buf, reinterpret_cast<const unsigned char *>(pcm) + lo_al, nbytes, &bars[warp]);
-            }
-            mbar_wait(&bars[warp], it & 1);
-        } else {
-            const u16 *g = pcm + (size_t)b * U;
-            u16 *d = reinterpret_cast<u16 *>(buf);
-            for (u32 i = lane; i < need; i += 32) d[i] = g[i];
-            __syncwarp();
-        }
-        VadWarpView v;
-        v.x = reinterpret_cast<const u16 *>(buf) + shift;
-        v.vec_ok = (shift & 7) == 0;
-
-        // ---- noise_atap, VAD.C:22-71 ------------------------------------------------------------
+    for (u32 b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
+        const size_t ubase = (size_t)b * U;
         atap_tag at = atap[b];
-        if (do_atap && n_len != 0 && (n_len % 240u) == 0 && n_len <= U) {     // VAD.C:33-36: else untouched
+        const bool atap_on = do_atap && n_len != 0 && (n_len % 240u) == 0 && n_len <= U;   // VAD.C:33-36: else untouched
+        // frames i = 0,80,.. while i < buf_len-160 (VAD.C:121); buf_len <= 160 reads past the buffer in the reference
+        // (int -> u32 compare) -- here: no frames.
+        u32 nfr = (do_vad && buf_len > SR_FRAME_LEN && buf_len <= U) ? (buf_len - SR_FRAME_LEN + SR_FRAME_MOV - 1) / SR_FRAME_MOV : 0;
+        const u32 nblk = nfr ? nfr + 1 : 0;                        // frame k = blocks k, k+1
+        const u32 vad_samples = 80u * nblk;                        // <= buf_len
+
+        // ---- noise_atap, VAD.C:22-71: from the first staged chunk when it fits, else straight from global ----------
+        const bool atap_staged = atap_on && n_len <= kVadChunk;
+        if (atap_on && !atap_staged) {
+            const u16 *g = pcm + ubase;
             u32 s = 0;
-            for (u32 i = lane; i < n_len; i += 32) s += v.x[i];
-            const u32 mid = warp_sum(s) / n_len;                               // VAD.C:41-45
+            for (u32 i = lane; i < n_len; i += 32) s += g[i];
+            const u32 mid = warp_sum(s) / n_len;
             u32 max_sum = 0, abs_sum = 0;
-            for (u32 i = 0; i < n_len; i += 240u) {                            // VAD.C:48-63
+            for (u32 i = 0; i < n_len; i += 240u) {
                 u32 mx = 0, sm = 0;
-                for (u32 h = lane; h < 240u; h += 32) {
-                    const u32 x = v.x[i + h], a = x > mid ? x - mid : mid - x;
-                    mx = max(mx, a); sm += a;
-                }
+                for (u32 h = lane; h < 240u; h += 32) { const u32 x = g[i + h], a = x > mid ? x - mid : mid - x; mx = max(mx, a); sm += a; }
                 max_sum += warp_max(mx);
                 abs_sum += sm;
             }
-            abs_sum = warp_sum(abs_sum);
-            abs_sum /= (n_len / SR_FRAME_LEN);                                 // VAD.C:65
-            max_sum /= (n_len / 240u);                                         // VAD.C:66
-            at.mid_val = mid;
-            at.n_thl = (u16)max_sum;                                           // n_thl_ratio 1, VAD.C:68
-            at.s_thl = abs_sum * 11u / 10u;                                    // s_thl_ratio 11/10, VAD.C:69
-            at.z_thl = 2;                                                      // 160*2/160/1, VAD.C:70
+            abs_sum = warp_sum(abs_sum) / (n_len / SR_FRAME_LEN);
+            max_sum /= (n_len / 240u);
+            at.mid_val = mid; at.n_thl = (u16)max_sum; at.s_thl = abs_sum * 11u / 10u; at.z_thl = 2;
             if (lane == 0) atap[b] = at;
         }
+        u32 mid = at.mid_val, a_thl = mid + at.n_thl, b_thl = mid - at.n_thl;            // VAD.C:112-113 (u32 wrap)
 
-        // ---- VAD, VAD.C:97-218 ------------------------------------------------------------------
+        // ---- stream the utterance in chunks of 32 blocks: one block per lane, every PCM byte read from HBM once ------
+        const u32 total = max(vad_samples, atap_staged ? n_len : 0u);
+        for (u32 c0 = 0; c0 < total; c0 += kVadChunk) {
+            const u32 cnt = min(kVadChunk, total - c0);
+            const int shift = stage_chunk(buf, pcm, total_bytes, base_aligned, ubase + c0, cnt, &bars[warp], phase, lane);
+            VadWarpView v;
+            v.x = reinterpret_cast<const u16 *>(buf) + shift;
+            v.vec_ok = (shift & 7) == 0;
+            if (c0 == 0 && atap_staged) {
+                u32 s = 0;
+                for (u32 i = lane; i < n_len; i += 32) s += v.x[i];
+                const u32 m = warp_sum(s) / n_len;                             // VAD.C:41-45
+                u32 max_sum = 0, abs_sum = 0;
+                for (u32 i = 0; i < n_len; i += 240u) {                        // VAD.C:48-63
+                    u32 mx = 0, sm = 0;
+                    for (u32 h = lane; h < 240u; h += 32) { const u32 x = v.x[i + h], a = x > m ? x - m : m - x; mx = max(mx, a); sm += a; }
+                    max_sum += warp_max(mx);
+                    abs_sum += sm;
+                }
+                abs_sum = warp_sum(abs_sum) / (n_len / SR_FRAME_LEN);          // VAD.C:65
+                max_sum /= (n_len / 240u);                                     // VAD.C:66
+                at.mid_val = m;
+                at.n_thl = (u16)max_sum;                                       // n_thl_ratio 1, VAD.C:68
+                at.s_thl = abs_sum * 11u / 10u;                                // s_thl_ratio 11/10, VAD.C:69
+                at.z_thl = 2;                                                  // 160*2/160/1, VAD.C:70
+                if (lane == 0) atap[b] = at;
+                mid = m; a_thl = mid + at.n_thl; b_thl = mid - at.n_thl;
+            }
+            const u32 blk = c0 / 80u + (u32)lane;
+            if (blk < nblk) {
+                u32 bs, fl;
+                block_scan(v, 80u * (u32)lane, mid, a_thl, b_thl, bs, fl);
+                info[2 * blk] = bs; info[2 * blk + 1] = fl;
+            }
+            __syncwarp();                                                      // buffer is re-staged next iteration
+        }
+
+        // ---- VAD, VAD.C:97-218: frames from the block summaries ---------------------------------------------------
         if (do_vad) {
-            const u32 mid = at.mid_val;
-            const u32 a_thl = mid + at.n_thl, b_thl = mid - at.n_thl;          // VAD.C:112-113 (u32 wrap)
-            // frames i = 0,80,.. while i < buf_len-160 (VAD.C:121); buf_len <= 160 reads past the buffer in
-            // the reference (int -> u32 compare) -- here: no frames.
-            u32 nfr = buf_len > SR_FRAME_LEN ? (buf_len - SR_FRAME_LEN + SR_FRAME_MOV - 1) / SR_FRAME_MOV : 0;
-            if (buf_len > U) nfr = 0;
             u32 seg[6] = {SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL, SR_SEG_NULL};
             if (nfr > 0) {
-                const u32 nblk = nfr + 1;                                      // frame k = blocks k, k+1
-                for (u32 blk = lane; blk < nblk; blk += 32) {
-                    u32 bs, fl;
-                    block_scan(v, 80u * blk, mid, a_thl, b_thl, bs, fl);
-                    info[2 * blk] = bs; info[2 * blk + 1] = fl;
-                }
-                __syncwarp();
                 u32 aw = 0;                                                    // lane j: activity of frames 32j..32j+31
                 u32 cin = 0;                                                   // class of last out-of-band sample before this pass
                 for (u32 k0 = 0, j = 0; k0 < nfr; k0 += 32, ++j) {
@@ -286,11 +315,7 @@ vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, in
 cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad,
                        atap_tag *atap, u32 *seg_off, int num_sms, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
-    u32 need = 0;
-    if (do_atap) need = n_len;
-    if (do_vad && buf_len > need) need = buf_len;
-    if (need > U) need = U;
-    const u32 buf_bytes = ((need * 2 + 32 + 127) / 128) * 128;
+    const u32 buf_bytes = ((kVadChunk * 2 + 32 + 127) / 128) * 128;   // one 32-block chunk + alignment slack
     const u32 max_frames = 2 * ((buf_len > 160 ? (buf_len - 160 + 79) / 80 : 0) + 2);   // 2 words per 80-sample block
     const size_t per_warp = (size_t)buf_bytes + (size_t)max_frames * 4;
     int warps = (int)((220 * 1024) / per_warp);
@@ -300,7 +325,9 @@ cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int
     cudaError_t e = cudaFuncSetAttribute(vad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);   // + 96 B static barriers <= 227 KB
     if (e != cudaSuccess) return e;
     u32 grid = (B + warps - 1) / warps;
-    const u32 cap = (u32)num_sms * 4;
+    size_t resident = (224 * 1024) / (smem + 2048);                     // CTAs that fit one SM (smem-limited)
+    if (resident < 1) resident = 1;
+    const u32 cap = (u32)num_sms * (u32)resident;                       // persistent: one wave, warps stride over utterances
     if (grid > cap) grid = cap;
     vad_kernel<<<grid, warps * 32, smem, st>>>(pcm, U, B, n_len, buf_len, do_atap, do_vad, atap, seg_off, buf_bytes,
                                               max_frames);
