@@ -30,16 +30,15 @@
 #include "sr_common.cuh"
 
 #ifndef SR_MFCC_DEFAULT_WARPS
-#define SR_MFCC_DEFAULT_WARPS 15
+#define SR_MFCC_DEFAULT_WARPS 16
 #endif
 
 namespace srk {
 
-constexpr int kNBuf = 3;
 constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
 constexpr int kFftWords = 1024 + 64;         // +4 words per 64
 
-template <int kConsumerWarps>
+template <int kConsumerWarps, int kNBuf>
 struct __align__(16) MfccSmem {
     unsigned char pcm[kNBuf][kPcmBufBytes];
     int2 tw[340 * 3];
@@ -76,13 +75,85 @@ __device__ __forceinline__ int mfcc_frames(u32 start, u32 end, u32 U) {
     return n > SR_VV_FRM_MAX ? 0 : (int)n;
 }
 
-template <int kConsumerWarps>
+// Stage utterance number `it` of this CTA's walk (batch row b) into ring slot it % kNBuf: one warp, lane 0 issues
+// the bulk copy. Bytes [lo,hi) of the batch = samples start-1 .. start+80(F-1)+159 of the utterance.
+template <int kConsumerWarps, int kNBuf, bool kRelaxedWait>
+__device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> &sm, int it, u32 b, const u16 *__restrict__ pcm,
+                                                u32 U, const u32 *__restrict__ seg, u32 seg_stride,
+                                                const atap_tag *__restrict__ atap, unsigned char *__restrict__ ftr,
+                                                const u32 *__restrict__ row_map, size_t total_bytes, bool base_aligned,
+                                                int lane) {
+    const int s = it % kNBuf;
+    const u32 st = seg[(size_t)b * seg_stride], en = seg[(size_t)b * seg_stride + 1];
+    const u32 mid = atap[b].mid_val;
+    const long long row = row_map ? (long long)row_map[b] : (long long)b;
+    if (it >= kNBuf) {
+        if (kRelaxedWait) mbar_wait_relaxed(&sm.empty[s], ((it / kNBuf) - 1) & 1);
+        else mbar_wait(&sm.empty[s], ((it / kNBuf) - 1) & 1);
+    }
+    const int F = mfcc_frames(st, en, U);
+    if (lane == 0) *reinterpret_cast<u16 *>(ftr + (size_t)b * kFtrBytes + 2) = (u16)F;   // MFCC.C:106,189
+    if (F == 0) {
+        if (lane == 0) { sm.meta[s][0] = 0; sm.meta[s][1] = 0; sm.meta[s][2] = (s32)mid; mbar_arrive(&sm.full[s]); }
+        return;
+    }
+    long long first = row * U + st - 1;                    // may be -1 for row 0, start 0
+    const long long last = row * U + st + 80ll * (F - 1) + 160;   // exclusive
+    unsigned char *dst = sm.pcm[s];
+    int off = 0;
+    if (first < 0) {                                       // x[-1] of the whole batch: reference reads
+        if (lane == 0) reinterpret_cast<u16 *>(dst)[7] = (u16)mid;   // out of bounds (MFCC.C:119); pinned to mid
+        first = 0; off = 8;                                // sample 0 lands at dst+16 (index 8), x[-1] at index 7
+        dst += 16;
+    }
+    const size_t lo = (size_t)first * 2, hi = (size_t)last * 2;
+    if (base_aligned) {
+        const size_t lo_al = lo & ~(size_t)15;
+        size_t hi_al = (hi + 15) & ~(size_t)15;
+        const size_t lim = total_bytes & ~(size_t)15;
+        if (hi_al > lim) hi_al = lim;
+        const u32 nbytes = (u32)(hi_al - lo_al);
+        const int shift = (int)((lo - lo_al) >> 1);
+        if (lane == 0) {
+            sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid;
+            sm.meta[s][1] = (off ? 7 : shift);             // index of x[start-1] (7 = slot just below dst+16)
+        }
+        // tail beyond the last whole 16-byte granule of the allocation: plain loads
+        if (hi > hi_al) {
+            const u16 *g = reinterpret_cast<const u16 *>(reinterpret_cast<const unsigned char *>(pcm) + hi_al);
+            u16 *d = reinterpret_cast<u16 *>(dst + (hi_al - lo_al));
+            const int n = (int)((hi - hi_al) >> 1);
+            if (lane < n) d[lane] = g[lane];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&sm.full[s], nbytes);
+            bulk_g2s(dst, reinterpret_cast<const unsigned char *>(pcm) + lo_al, nbytes, &sm.full[s]);
+        }
+    } else {                                               // unaligned batch base: cooperative plain copy
+        const u16 *g = pcm + first;
+        u16 *d = reinterpret_cast<u16 *>(dst);
+        const int n = (int)(last - first);
+        for (int i = lane; i < n; i += 32) d[i] = g[i];
+        __syncwarp();
+        if (lane == 0) {
+            sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid; sm.meta[s][1] = off ? 7 : 0;
+            mbar_arrive(&sm.full[s]);
+        }
+    }
+}
+
+// kSelf = false: warp kConsumerWarps is a dedicated producer. kSelf = true: every warp is a consumer and the staging
+// of utterance it+kAhead is a side job of warp it % kConsumerWarps at the top of iteration it, so all four
+// schedulers of the SM carry the same number of working warps.
+template <int kConsumerWarps, int kNBuf, bool kSelf>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
                                           unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
                                           const u32 *__restrict__ row_map, u32 rows_total) {
+    constexpr int kAhead = kNBuf - 2;                      // slot of it+kAhead was last used by utterance it-2
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MfccSmem<kConsumerWarps> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps> *>(smem_raw);
+    MfccSmem<kConsumerWarps, kNBuf> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps, kNBuf> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time: tables to shared memory, barriers ------------------------------------------
@@ -99,68 +170,20 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     const size_t total_bytes = (size_t)(row_map ? rows_total : B) * U * 2;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
 
-    // ================================ producer warp =============================================
-    if (warp == kConsumerWarps) {
-        int it = 0;
-        for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it) {
-            const int s = it % kNBuf;
-            if (it >= kNBuf) mbar_wait_relaxed(&sm.empty[s], ((it / kNBuf) - 1) & 1);
-            const u32 st = seg[(size_t)b * seg_stride], en = seg[(size_t)b * seg_stride + 1];
-            const int F = mfcc_frames(st, en, U);
-            const u32 mid = atap[b].mid_val;
-            if (lane == 0) *reinterpret_cast<u16 *>(ftr + (size_t)b * kFtrBytes + 2) = (u16)F;   // MFCC.C:106,189
-            if (F == 0) {
-                if (lane == 0) { sm.meta[s][0] = 0; sm.meta[s][1] = 0; sm.meta[s][2] = (s32)mid; mbar_arrive(&sm.full[s]); }
-                continue;
-            }
-            // bytes [lo,hi) of the batch: samples start-1 .. start+80(F-1)+159 of utterance b
-            const long long row = row_map ? (long long)row_map[b] : (long long)b;
-            long long first = row * U + st - 1;                    // may be -1 for row 0, start 0
-            const long long last = row * U + st + 80ll * (F - 1) + 160;   // exclusive
-            unsigned char *dst = sm.pcm[s];
-            int off = 0;
-            if (first < 0) {                                       // x[-1] of the whole batch: reference reads
-                if (lane == 0) reinterpret_cast<u16 *>(dst)[7] = (u16)mid;   // out of bounds (MFCC.C:119); pinned to mid
-                first = 0; off = 8;                                // sample 0 lands at dst+16 (index 8), x[-1] at index 7
-                dst += 16;
-            }
-            const size_t lo = (size_t)first * 2, hi = (size_t)last * 2;
-            if (base_aligned) {
-                const size_t lo_al = lo & ~(size_t)15;
-                size_t hi_al = (hi + 15) & ~(size_t)15;
-                const size_t lim = total_bytes & ~(size_t)15;
-                if (hi_al > lim) hi_al = lim;
-                const u32 nbytes = (u32)(hi_al - lo_al);
-                const int shift = (int)((lo - lo_al) >> 1);
-                if (lane == 0) {
-                    sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid;
-                    sm.meta[s][1] = (off ? 7 : shift);             // index of x[start-1] (7 = slot just below dst+16)
-                }
-                // tail beyond the last whole 16-byte granule of the allocation: plain loads
-                if (hi > hi_al) {
-                    const u16 *g = reinterpret_cast<const u16 *>(reinterpret_cast<const unsigned char *>(pcm) + hi_al);
-                    u16 *d = reinterpret_cast<u16 *>(dst + (hi_al - lo_al));
-                    const int n = (int)((hi - hi_al) >> 1);
-                    if (lane < n) d[lane] = g[lane];
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&sm.full[s], nbytes);
-                    bulk_g2s(dst, reinterpret_cast<const unsigned char *>(pcm) + lo_al, nbytes, &sm.full[s]);
-                }
-            } else {                                               // unaligned batch base: cooperative plain copy
-                const u16 *g = pcm + first;
-                u16 *d = reinterpret_cast<u16 *>(dst);
-                const int n = (int)(last - first);
-                for (int i = lane; i < n; i += 32) d[i] = g[i];
-                __syncwarp();
-                if (lane == 0) {
-                    sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid; sm.meta[s][1] = off ? 7 : 0;
-                    mbar_arrive(&sm.full[s]);
-                }
-            }
+    if (!kSelf) {
+        // ============================ producer warp =============================================
+        if (warp == kConsumerWarps) {
+            int it = 0;
+            for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it)
+                stage_utterance<kConsumerWarps, kNBuf, true>(sm, it, b, pcm, U, seg, seg_stride, atap, ftr, row_map,
+                                                             total_bytes, base_aligned, lane);
+            return;
         }
-        return;
+    } else if (warp < kAhead) {                            // prologue: utterances 0 .. kAhead-1
+        const u32 b = blockIdx.x + (u32)warp * gridDim.x;
+        if (b < B)
+            stage_utterance<kConsumerWarps, kNBuf, false>(sm, warp, b, pcm, U, seg, seg_stride, atap, ftr, row_map,
+                                                          total_bytes, base_aligned, lane);
     }
 
     // ================================ consumer warps ============================================
@@ -182,6 +205,12 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     u32 gidx = 0;   // frames of this CTA's stream before the current utterance
     int it = 0;
     for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+        if (kSelf && warp == it % kConsumerWarps) {
+            const u32 bn = b + (u32)kAhead * gridDim.x;
+            if (bn < B)
+                stage_utterance<kConsumerWarps, kNBuf, false>(sm, it + kAhead, bn, pcm, U, seg, seg_stride, atap, ftr,
+                                                              row_map, total_bytes, base_aligned, lane);
+        }
         const int s = it % kNBuf;
         mbar_wait(&sm.full[s], (it / kNBuf) & 1);
         const int F = sm.meta[s][0];
@@ -339,22 +368,20 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     }
 }
 
-// Variants: consumer warps per CTA x register cap (one persistent CTA per SM). More warps fill issue slots that
-// stay idle when only 4 warps per scheduler are resident; fewer registers cost a few spills.
-#define SR_MFCC_VARIANT(W, NREG)                                                                                  \
-    __global__ void __maxnreg__(NREG) mfcc_kernel_w##W(const u16 *__restrict__ pcm, u32 U, u32 B,               \
-                                                       const u32 *__restrict__ seg, u32 seg_stride,              \
-                                                       const atap_tag *__restrict__ atap,                         \
-                                                       unsigned char *__restrict__ ftr,                           \
-                                                       const DevTables *__restrict__ tab,                         \
-                                                       const u32 *__restrict__ row_map, u32 rows_total) {        \
-        mfcc_body<W>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total);                            \
+// Variants (one persistent CTA per SM; threads per CTA are capped at floor(65536 / regs / 128) * 128):
+//   s16: 16 warps, all consumers, staging as a rotating side job, 4-deep ring   (default)
+//   w15: 15 consumers + 1 dedicated producer warp, 3-deep ring
+#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG)                                                                  \
+    __global__ void __maxnreg__(NREG) mfcc_kernel_##NAME(const u16 *__restrict__ pcm, u32 U, u32 B,              \
+                                                         const u32 *__restrict__ seg, u32 seg_stride,            \
+                                                         const atap_tag *__restrict__ atap,                       \
+                                                         unsigned char *__restrict__ ftr,                         \
+                                                         const DevTables *__restrict__ tab,                       \
+                                                         const u32 *__restrict__ row_map, u32 rows_total) {      \
+        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total);                  \
     }
-// threads per CTA are capped at floor(65536 / regs / 128) * 128, so consumer warps + 1 producer = 16 / 20 / 24 / 28
-SR_MFCC_VARIANT(15, 128)
-SR_MFCC_VARIANT(19, 96)
-SR_MFCC_VARIANT(23, 80)
-SR_MFCC_VARIANT(27, 72)
+SR_MFCC_VARIANT(s16, 16, 4, true, 128)
+SR_MFCC_VARIANT(w15, 15, 3, false, 128)
 
 // ---- generic (unpruned) FFT + magnitude: the reference's global `fft` (MFCC.C:27-62) -----------
 // One warp per frame, all five passes in shared memory exactly as the asm orders them. Not on the
@@ -409,22 +436,24 @@ fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, cons
 }
 
 // ---- host launchers -----------------------------------------------------------------------------
-template <int W, typename K>
+template <int W, int NB, bool SELF, typename K>
 static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride,
                                        const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st,
                                        const u32 *row_map, u32 rows_total) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfccSmem<W>));
+    const size_t smem = sizeof(MfccSmem<W, NB>);
+    const int threads = (SELF ? W : W + 1) * 32;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
-    kern<<<grid, (W + 1) * 32, sizeof(MfccSmem<W>), st>>>(pcm, U, B, seg, seg_stride, atap,
-                                                         static_cast<unsigned char *>(ftr), tab, row_map, rows_total);
+    kern<<<grid, threads, smem, st>>>(pcm, U, B, seg, seg_stride, atap, static_cast<unsigned char *>(ftr), tab, row_map,
+                                      rows_total);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess)
-            fprintf(stderr, "mfcc_kernel_w%d launch failed (%s): regs %d, maxThreads %d, static smem %zu, dyn smem %zu (max %d), threads %d\n",
-                    W, cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, sizeof(MfccSmem<W>),
-                    fa.maxDynamicSharedSizeBytes, (W + 1) * 32);
+            fprintf(stderr, "mfcc kernel (%d warps) launch failed (%s): regs %d, maxThreads %d, static smem %zu, dyn smem %zu (max %d), threads %d\n",
+                    W, cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, smem,
+                    fa.maxDynamicSharedSizeBytes, threads);
     }
     return e;
 }
@@ -434,17 +463,14 @@ cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_st
     if (B == 0) return cudaSuccess;
     const DevTables *tab = dev_tables();
     if (!tab) return cudaErrorInitializationError;
-    static int variant = -1;                               // SR_MFCC_WARPS=15|19|23|27 selects a variant (tuning knob)
+    static int variant = -1;                               // SR_MFCC_WARPS=15 selects the dedicated-producer variant (tuning knob)
     if (variant < 0) {
         const char *ev = getenv("SR_MFCC_WARPS");
         variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
     }
-    switch (variant) {
-    case 23: return launch_mfcc_variant<23>(mfcc_kernel_w23, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
-    case 27: return launch_mfcc_variant<27>(mfcc_kernel_w27, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
-    default: return launch_mfcc_variant<15>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
-    case 19: return launch_mfcc_variant<19>(mfcc_kernel_w19, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
-    }
+    if (variant == 15)
+        return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
+    return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
 }
 
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
