@@ -557,6 +557,22 @@ def main():
                  status=status[:S].cpu().numpy(), score=score[:S].cpu().numpy().view(np.uint32).reshape(-1))
         parity = all(np.array_equal(g[k], np.asarray(out[k]).reshape(-1)) for k in g)
 
+    # integer-issue view of the dominant kernel: warp instructions per frame (ncu smsp__inst_executed.sum / frames,
+    # a property of the SASS, profiles/r1_traffic.json) x frames of this launch / live kernel time, against
+    # 4 schedulers x SMs x the SM clock sampled under load. This, not HBM, is what bounds the bit-exact FFT.
+    try:
+        wipf = float(tj["mfcc_warp_inst_per_frame"])
+        clk = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 0.0)
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        if clk > 0:
+            ipeak = n_sms * 4 * clk * 1e6
+            iach = wipf * frames_rank0 / (kern_ms["mfcc"] * 1e-3)
+            roofline["int_issue"] = {"achieved": iach / 1e9, "peak": ipeak / 1e9, "unit": "G warp-inst/s", "frac": iach / ipeak,
+                                     "warp_inst_per_frame": wipf,
+                                     "note": "ALU and FMA-heavy (IMAD) pipes are half rate: both sit at ~65 % (profiles/)"}
+    except Exception:
+        pass
+
     total_utts = B * world
     line = {
         "metric": "utterances/s", "value": total_utts / (ms_step * 1e-3), "unit": "utterances/s", "n_gpus": world,

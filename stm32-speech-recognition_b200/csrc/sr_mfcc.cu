@@ -2,11 +2,12 @@
 // fixed-point radix-4 FFT of Src/BSP/cr4_fft_1024_stm32.s:95-281 done in registers/shared memory.
 //
 // Work decomposition (B200: 148 SMs, one persistent CTA per SM):
-//   * a CTA walks utterances b = blockIdx.x, +gridDim.x, ...; a PRODUCER warp stages each
-//     utterance's PCM segment [start-1, end) into a 3-deep shared-memory ring with 1-D bulk
-//     async copies (TMA engine, cp.async.bulk + mbarrier complete_tx), so every PCM sample is
-//     read from HBM exactly once although frames overlap by 50 %;
-//   * 15 CONSUMER warps (see the variant table below) take frames round-robin from the CTA's concatenated frame stream,
+//   * a CTA walks utterances b = blockIdx.x, +gridDim.x, ...; each utterance's PCM segment
+//     [start-1, end) is staged into a 4-deep shared-memory ring with 1-D bulk async copies (TMA
+//     engine, cp.async.bulk + mbarrier complete_tx), two utterances ahead, as a side job that
+//     rotates over the warps -- every PCM sample is read from HBM exactly once although frames
+//     overlap by 50 %;
+//   * all 16 warps (see the variant table below) take frames round-robin from the CTA's concatenated frame stream,
 //     one frame per warp: pre-emphasis + Hamming (MFCC.C:115-124), FFT, |.| (MFCC.C:49-60),
 //     energy (MFCC.C:128-133), 24 triangular filters (MFCC.C:136-162), log (MFCC.C:165-170),
 //     DCT (MFCC.C:173-183) -> 12 x s16.
@@ -370,7 +371,10 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 
 // Variants (one persistent CTA per SM; threads per CTA are capped at floor(65536 / regs / 128) * 128):
 //   s16: 16 warps, all consumers, staging as a rotating side job, 4-deep ring   (default)
-//   w15: 15 consumers + 1 dedicated producer warp, 3-deep ring
+//   w15: 15 consumers + 1 dedicated producer warp, 3-deep ring   (SR_MFCC_WARPS=15; 5 % slower: one scheduler
+//        carries only 3 working warps)
+// Measured and dropped: 20 warps @ 96 regs (5.29 ms vs 5.31), 24 warps @ 80 regs (5.48 ms) -- the half-rate ALU and
+// FMA-heavy pipes, not occupancy, bound the kernel.
 #define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG)                                                                  \
     __global__ void __maxnreg__(NREG) mfcc_kernel_##NAME(const u16 *__restrict__ pcm, u32 U, u32 B,              \
                                                          const u32 *__restrict__ seg, u32 seg_stride,            \

@@ -19,7 +19,7 @@
 
 namespace srk {
 
-constexpr int kVadMaxWarps = 32;
+constexpr int kVadMaxWarps = 20;
 
 struct VadWarpView {
     const u16 *x;       // staged samples, x[0] = first sample of the utterance
@@ -37,72 +37,192 @@ __device__ __forceinline__ u32 warp_max(u32 v) {
     return v;
 }
 
+// noise_atap's three sums (VAD.C:41-63) over staged samples x[0, n_len), n_len % 240 == 0: mid = sum/n_len,
+// max_sum = sum over 240-sample blocks of max|x-mid|, abs_sum = sum |x-mid|. Vector form: lane l owns samples
+// [80l, 80l+80) (three lanes per 240-block, n_len <= 2560), 16-byte loads, IDP.2A for the plain sum.
+__device__ __forceinline__ void atap_stats(const u16 *x, bool vec_ok, u32 n_len, int lane, u32 &mid_out, u32 &max_sum_out,
+                                           u32 &abs_sum_out) {
+    if (vec_ok && n_len <= 2560u) {
+        const bool act = 80u * (u32)lane < n_len;
+        const uint4 *p = reinterpret_cast<const uint4 *>(x + (act ? 80 * lane : 0));
+        u32 s = 0;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            const uint4 q = p[c];
+            s = __dp2a_lo(q.x, 0x0101u, s); s = __dp2a_lo(q.y, 0x0101u, s);
+            s = __dp2a_lo(q.z, 0x0101u, s); s = __dp2a_lo(q.w, 0x0101u, s);
+        }
+        const u32 mid = warp_sum(act ? s : 0u) / n_len;
+        u32 mx = 0, sm = 0;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            const uint4 q = p[c];
+            const u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const u32 v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFFu);
+                const u32 d = __usad(v, mid, 0u);
+                mx = max(mx, d); sm += d;
+            }
+        }
+        if (!act) { mx = 0; sm = 0; }
+        const u32 m1 = __shfl_down_sync(0xFFFFFFFFu, mx, 1), m2 = __shfl_down_sync(0xFFFFFFFFu, mx, 2);
+        const u32 bmax = (act && lane % 3 == 0) ? max(mx, max(m1, m2)) : 0u;      // lanes 3k..3k+2 = block k
+        mid_out = mid;
+        max_sum_out = warp_sum(bmax);
+        abs_sum_out = warp_sum(sm);
+        return;
+    }
+    u32 s = 0;
+    for (u32 i = lane; i < n_len; i += 32) s += x[i];
+    const u32 mid = warp_sum(s) / n_len;                             // VAD.C:41-45
+    u32 max_sum = 0, abs_sum = 0;
+    for (u32 i = 0; i < n_len; i += 240u) {                          // VAD.C:48-63
+        u32 mx = 0, sm = 0;
+        for (u32 h = lane; h < 240u; h += 32) { const u32 v = x[i + h], a = v > mid ? v - mid : mid - v; mx = max(mx, a); sm += a; }
+        max_sum += warp_max(mx);
+        abs_sum += sm;
+    }
+    mid_out = mid; max_sum_out = max_sum; abs_sum_out = warp_sum(abs_sum);
+}
+
 // per-block summary: bs = sum |x-mid| over the 80 samples; flags = zc (bits 0..6, alternations inside the
 // block) | lc << 7 (class of last out-of-band sample, 0 none / 1 below / 2 above) | lcA << 9 (same over the
 // first 79 samples) | p0 << 11 (sample 0 is out of band)
-// Word-level alternation count. H / L = bitmaps (bit i = sample i) of the samples above / below the band
-// (disjoint), `last` = class (0 none / 1 below / 2 above) of the last out-of-band sample before bit 0 of this
-// word -- 0 means "unknown" and never counts (the frame-level pass applies the carried-in state separately).
-// Returns the number of out-of-band samples whose class differs from the previous out-of-band sample's and
-// updates `last`. The previous class of every position comes from a segmented forward fill of H over the
-// markers N = H|L (5 doubling steps) instead of a per-sample state machine.
-__device__ __forceinline__ u32 word_alternations(u32 H, u32 L, u32 &last) {
-    const u32 N = H | L;
-    u32 P = H, K = ~N;
+//
+// flags of one 80-sample block from its bitmaps (H = ">= a_thl", L = "< b_thl", bit i = sample i; words 0..31, 32..63,
+// 64..79). An alternation is an out-of-band sample ("marker", N = H|L) whose class differs from the previous marker's;
+// the first marker of the block never counts here (the frame-level pass applies the carried-in state). "Previous
+// marker is H" for every position comes from ONE 80-bit addition: in (H << 1) + ~N a carry injected just above each
+// H marker ripples through the non-markers and lands on the next marker. Bit 80 of the sum says the last marker of the
+// block is H; bit 79, xor-ed with ~N, says the same for the first 79 samples.
+__device__ __forceinline__ u32 block_flags(u32 (&H)[3], u32 (&L)[3]) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { P |= K & (P << d); K &= K << d; }
-    // P[i]: the most recent marker at or before i is "above"
-    const u32 low = N & (0u - N);                       // lowest marker
-    const u32 seen = ~(low | (low - 1u));               // positions strictly above the lowest marker (0 if N == 0)
-    const u32 in2 = last == 2u ? 0xFFFFFFFFu : 0u, in1 = last == 1u ? 0xFFFFFFFFu : 0u;
-    const u32 prevH = ((P << 1) & seen) | (~seen & in2);
-    const u32 prevL = (~(P << 1) & seen) | (~seen & in1);
-    const u32 alt = (H & prevL) | (L & prevH);
-    if (N) last = ((H >> (31 - __clz(N))) & 1u) ? 2u : 1u;
-    return __popc(alt);
+    for (int k = 0; k < 3; ++k) L[k] &= ~H[k];                              // ">= a" is tested first, "< b" only else
+    const u32 n0 = ~(H[0] | L[0]), n1 = ~(H[1] | L[1]), n2 = ~(H[2] | L[2]) & 0xFFFFu;   // bit 80 acts as a marker
+    u32 sh0, sh1, sh2, sl0, sl1, sl2;
+    asm("{\n add.cc.u32 %0, %3, %6;\n addc.cc.u32 %1, %4, %7;\n addc.u32 %2, %5, %8;\n}"
+        : "=r"(sh0), "=r"(sh1), "=r"(sh2)
+        : "r"(H[0] << 1), "r"(__funnelshift_l(H[0], H[1], 1)), "r"(__funnelshift_l(H[1], H[2], 1)), "r"(n0), "r"(n1), "r"(n2));
+    asm("{\n add.cc.u32 %0, %3, %6;\n addc.cc.u32 %1, %4, %7;\n addc.u32 %2, %5, %8;\n}"
+        : "=r"(sl0), "=r"(sl1), "=r"(sl2)
+        : "r"(L[0] << 1), "r"(__funnelshift_l(L[0], L[1], 1)), "r"(__funnelshift_l(L[1], L[2], 1)), "r"(n0), "r"(n1), "r"(n2));
+    const u32 zc = __popc((L[0] & sh0) | (H[0] & sl0)) + __popc((L[1] & sh1) | (H[1] & sl1)) +
+                   __popc((L[2] & sh2) | (H[2] & sl2));
+    const u32 last = ((sh2 >> 15) & 2u) | ((sl2 >> 16) & 1u);               // bit 16 of word 2 = position 80
+    const u32 lastA = (((sh2 ^ n2) >> 14) & 2u) | (((sl2 ^ n2) >> 15) & 1u); // position 79
+    const u32 p0 = ~n0 & 1u;
+    return zc | (last << 7) | (lastA << 9) | (p0 << 11);
 }
 
-// Per-block summary, built from bitmaps: per sample only 1 extract + 1 VABSDIFF + 2 compares + 2 predicated ORs.
+// Per-block summary, built from bitmaps. Two samples per 32-bit word stay packed: |x-mid| = max - min per 16-bit lane
+// (VIMNMX.U16x2), summed by IDP.2A; the band compares are carries of w + (0 - (t << 16)) (high sample) and
+// (w << 16) + (0 - (t << 16)) (low sample, one LEA), shifted MSB-first into the bitmaps by IMAD.X (x*2 + carry, FMA pipe):
+// per sample 3 ALU-pipe and 3 FMA-pipe instructions -- the ALU pipe is what bounds this kernel. t == 0 and t > 0xFFFF
+// are patched after the loop; mid > 0xFFFF (only possible with a caller-supplied atap_tag) takes the plain loop.
 __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid, u32 a_thl, u32 b_thl, u32 &bs_out,
                                            u32 &flags_out) {
     u32 bs = 0;
-    u32 H[3] = {0, 0, 0}, L[3] = {0, 0, 0};            // samples 0..31, 32..63, 64..79
+    u32 H[3], L[3];
     const u16 *p = v.x + i0;
+    if (mid <= 0xFFFFu) {
+        u32 gA[3] = {0, 0, 0}, gB[3] = {0, 0, 0};      // "s >= a_thl", "s >= b_thl"; samples 0..31, 32..63, 64..79
+        const u32 mid2 = mid | (mid << 16), na = 0u - (a_thl << 16), nb = 0u - (b_thl << 16);
 #pragma unroll
-    for (int c = 0; c < 10; ++c) {
-        u32 w[4];
-        if (v.vec_ok) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(p + 8 * c);
-            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
-        } else {
+        for (int c = 0; c < 10; ++c) {
+            u32 w[4];
+            if (v.vec_ok) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(p + 8 * c);
+                w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = (u32)p[8 * c + 2 * j] | ((u32)p[8 * c + 2 * j + 1] << 16);
+                for (int j = 0; j < 4; ++j) w[j] = (u32)p[8 * c + 2 * j] | ((u32)p[8 * c + 2 * j + 1] << 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g = (8 * c + 2 * j) >> 5;
+                u32 mx, mn;
+                asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(w[j]), "r"(mid2));
+                asm("min.u16x2 %0, %1, %2;" : "=r"(mn) : "r"(w[j]), "r"(mid2));
+                bs = __dp2a_lo(mx - mn, 0x0101u, bs);                       // VAD.C:126-129
+                asm("{\n .reg .u32 t, l;\n shl.b32 l, %2, 16;\n"
+                    " add.cc.u32 t, l, %3;\n madc.lo.u32 %0, %0, 2, 0;\n"  // VAD.C:134-141 / 143-156, low sample
+                    " add.cc.u32 t, l, %4;\n madc.lo.u32 %1, %1, 2, 0;\n"
+                    " add.cc.u32 t, %2, %3;\n madc.lo.u32 %0, %0, 2, 0;\n" // high sample
+                    " add.cc.u32 t, %2, %4;\n madc.lo.u32 %1, %1, 2, 0;\n}"
+                    : "+r"(gA[g]), "+r"(gB[g])
+                    : "r"(w[j]), "r"(na), "r"(nb));
+            }
         }
+        H[0] = __brev(gA[0]); H[1] = __brev(gA[1]); H[2] = __brev(gA[2]) >> 16;
+        L[0] = ~__brev(gB[0]); L[1] = ~__brev(gB[1]); L[2] = ~(__brev(gB[2]) >> 16) & 0xFFFFu;
+        if (a_thl == 0) { H[0] = 0xFFFFFFFFu; H[1] = 0xFFFFFFFFu; H[2] = 0xFFFFu; }   // s >= 0 always
+        if (a_thl > 0xFFFFu) { H[0] = 0; H[1] = 0; H[2] = 0; }                         // s >= t never
+        if (b_thl == 0) { L[0] = 0; L[1] = 0; L[2] = 0; }                              // s <  0 never
+        if (b_thl > 0xFFFFu) { L[0] = 0xFFFFFFFFu; L[1] = 0xFFFFFFFFu; L[2] = 0xFFFFu; }   // s <  t always
+    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int h = 8 * c + j;
-            const u32 s = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu);
-            bs = __usad(s, mid, bs);                                        // VAD.C:126-129
-            if (s >= a_thl) H[h >> 5] |= 1u << (h & 31);                    // VAD.C:134-141 / 143-156
-            if (s < b_thl) L[h >> 5] |= 1u << (h & 31);
+        for (int k = 0; k < 3; ++k) {
+            u32 hw = 0, lw = 0;
+            const int n = k < 2 ? 32 : 16;
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) {
+                const u32 s = p[32 * k + i];
+                bs = __usad(s, mid, bs);
+                hw |= (s >= a_thl ? 1u : 0u) << i;
+                lw |= (s < b_thl ? 1u : 0u) << i;
+            }
+            H[k] = hw; L[k] = lw;
         }
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) L[k] &= ~H[k];                              // ">= a" is tested first, "< b" only else
-    u32 last = 0, zc = 0;
-    zc += word_alternations(H[0], L[0], last);
-    zc += word_alternations(H[1], L[1], last);
-    u32 lastA = last;                                                       // state after sample 63
-    const u32 zc2 = word_alternations(H[2], L[2], last);
-    zc += zc2;
-    // last class among the first 79 samples: redo the (cheap) "last" update of word 2 without sample 79 (bit 15)
-    {
-        const u32 Hm = H[2] & 0x7FFFu, Nm = (H[2] | L[2]) & 0x7FFFu;
-        if (Nm) lastA = ((Hm >> (31 - __clz(Nm))) & 1u) ? 2u : 1u;
-    }
-    const u32 p0 = (H[0] | L[0]) & 1u;
     bs_out = bs;
-    flags_out = zc | (last << 7) | (lastA << 9) | (p0 << 11);
+    flags_out = block_flags(H, L);
+}
+
+// The same summary for up to four blocks at once, eight lanes per block (ten samples each): used for the last pass of
+// an utterance when only a few blocks remain, instead of a full 80-sample pass with most lanes idle. x must be
+// 4-byte aligned. Every lane of a group returns the group's result; groups >= nblocks return garbage.
+__device__ __forceinline__ void block_scan_split8(const u16 *x, int lane, u32 nblocks, u32 mid, u32 a_thl, u32 b_thl,
+                                                  u32 &bs_out, u32 &flags_out) {
+    const int g = lane >> 3, j = lane & 7;
+    const bool act = (u32)g < nblocks;
+    const u32 *pw = reinterpret_cast<const u32 *>(x + (act ? 80 * g + 10 * j : 0));
+    const u32 na = 0u - a_thl, nb = 0u - b_thl;
+    u32 bs = 0, gA = 0, gB = 0;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const u32 w = pw[c];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const u32 s = k ? (w >> 16) : (w & 0xFFFFu);
+            bs = __usad(s, mid, bs);
+            asm("{\n .reg .u32 t;\n"
+                " add.cc.u32 t, %2, %3;\n madc.lo.u32 %0, %0, 2, 0;\n"
+                " add.cc.u32 t, %2, %4;\n madc.lo.u32 %1, %1, 2, 0;\n}"
+                : "+r"(gA), "+r"(gB)
+                : "r"(s), "r"(na), "r"(nb));
+        }
+    }
+    u32 h10 = __brev(gA) >> 22, l10 = ~(__brev(gB) >> 22) & 0x3FFu;       // sample i of this lane at bit i
+    if (a_thl == 0) h10 = 0x3FFu;
+    if (b_thl == 0) l10 = 0;
+    // place the 10 bits at position 10*j of the 80-bit block bitmap, then OR / add over the group's 8 lanes
+    const int pos = 10 * j;
+    const u64 hv = pos < 64 ? ((u64)h10 << pos) : 0ull, lv = pos < 64 ? ((u64)l10 << pos) : 0ull;
+    u32 H[3], L[3];
+    H[0] = (u32)hv; H[1] = (u32)(hv >> 32); H[2] = pos < 64 ? (pos > 54 ? h10 >> (64 - pos) : 0u) : (h10 << (pos - 64));
+    L[0] = (u32)lv; L[1] = (u32)(lv >> 32); L[2] = pos < 64 ? (pos > 54 ? l10 >> (64 - pos) : 0u) : (l10 << (pos - 64));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            H[k] |= __shfl_xor_sync(0xFFFFFFFFu, H[k], o);
+            L[k] |= __shfl_xor_sync(0xFFFFFFFFu, L[k], o);
+        }
+        bs += __shfl_xor_sync(0xFFFFFFFFu, bs, o);
+    }
+    bs_out = bs;
+    flags_out = block_flags(H, L);
 }
 
 // position of the first set bit at index >= from in a bitmap held one 32-bit word per lane; -1 if none
@@ -123,11 +243,11 @@ __device__ __forceinline__ u32 bm_shr(u32 x, int s, int lane) {
     return (x >> s) | (nxt << (32 - s));
 }
 
-// stage samples [first, first+count) of the batch into `buf` (bulk async copy when the batch base is 16-byte
-// aligned, plain loads otherwise); returns the sample index of `first` inside buf
-__device__ __forceinline__ int stage_chunk(unsigned char *buf, const u16 *pcm, size_t total_bytes, bool base_aligned,
-                                           size_t first, u32 count, u64 *bar, u32 &phase, int lane) {
-    if (count == 0) return 0;
+// start staging samples [first, first+count) of the batch into `buf` (bulk async copy when the batch base is 16-byte
+// aligned, plain loads otherwise); completion is one phase of `bar` either way. Returns the sample index of `first`
+// inside buf.
+__device__ __forceinline__ int chunk_issue(unsigned char *buf, const u16 *pcm, size_t total_bytes, bool base_aligned,
+                                           size_t first, u32 count, u64 *bar, int lane) {
     const size_t lo = first * 2, hi = lo + (size_t)count * 2;
     if (base_aligned) {
         const size_t lo_al = lo & ~(size_t)15;
@@ -147,14 +267,13 @@ __device__ __forceinline__ int stage_chunk(unsigned char *buf, const u16 *pcm, s
             mbar_arrive_expect_tx(bar, nbytes);
             bulk_g2s(buf, reinterpret_cast<const unsigned char *>(pcm) + lo_al, nbytes, bar);
         }
-        mbar_wait(bar, phase & 1u);
-        ++phase;
         return shift;
     }
     const u16 *g = pcm + first;
     u16 *d = reinterpret_cast<u16 *>(buf);
     for (u32 i = lane; i < count; i += 32) d[i] = g[i];
     __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
     return 0;
 }
 
@@ -164,69 +283,70 @@ __global__ void __launch_bounds__(kVadMaxWarps * 32)
 vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad,
            atap_tag *__restrict__ atap, u32 *__restrict__ seg_off, u32 buf_bytes, u32 max_frames) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ u64 bars[kVadMaxWarps];
+    __shared__ u64 bars[kVadMaxWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    unsigned char *buf = smem_raw + (size_t)warp * buf_bytes;
-    u32 *info = reinterpret_cast<u32 *>(smem_raw + (size_t)nwarps * buf_bytes) + (size_t)warp * max_frames;
-    if (lane == 0) mbar_init(&bars[warp], 1);
+    unsigned char *buf0 = smem_raw + (size_t)warp * 2 * buf_bytes, *buf1 = buf0 + buf_bytes;   // double buffer
+    u32 *info = reinterpret_cast<u32 *>(smem_raw + (size_t)nwarps * 2 * buf_bytes) + (size_t)warp * max_frames;
+    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
 
     const size_t total_bytes = (size_t)B * U * 2;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
-    u32 phase = 0;                                                 // completed bulk copies of this warp's barrier
 
-    for (u32 b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
+    // the same for every utterance of the launch
+    const bool atap_on = do_atap && n_len != 0 && (n_len % 240u) == 0 && n_len <= U;   // VAD.C:33-36: else untouched
+    // frames i = 0,80,.. while i < buf_len-160 (VAD.C:121); buf_len <= 160 reads past the buffer in the reference
+    // (int -> u32 compare) -- here: no frames.
+    const u32 nfr = (do_vad && buf_len > SR_FRAME_LEN && buf_len <= U) ? (buf_len - SR_FRAME_LEN + SR_FRAME_MOV - 1) / SR_FRAME_MOV : 0;
+    const u32 nblk = nfr ? nfr + 1 : 0;                            // frame k = blocks k, k+1
+    const u32 vad_samples = 80u * nblk;                            // <= buf_len
+    const bool atap_staged = atap_on && n_len <= kVadChunk;        // noise_atap from the first staged chunk
+    const u32 total = max(vad_samples, atap_staged ? n_len : 0u);  // samples staged per utterance
+
+    // The warp's chunks (utterance b, b+stride, ..; 32 blocks each) form one stream through the two buffers: chunk k+1
+    // is in flight while chunk k is scanned, across utterance boundaries too. Every PCM byte is read from HBM once.
+    const u32 stride = gridDim.x * nwarps;
+    u32 b = blockIdx.x * nwarps + warp;
+    u32 k = 0, ph0 = 0, ph1 = 0;                                   // chunk counter, completed phases per buffer
+    int shift_cur = 0, shift_nxt = 0;
+    if (total && b < B)
+        shift_cur = chunk_issue(buf0, pcm, total_bytes, base_aligned, (size_t)b * U, min(kVadChunk, total), &bars[warp][0], lane);
+
+    for (; b < B; b += stride) {
         const size_t ubase = (size_t)b * U;
         atap_tag at = atap[b];
-        const bool atap_on = do_atap && n_len != 0 && (n_len % 240u) == 0 && n_len <= U;   // VAD.C:33-36: else untouched
-        // frames i = 0,80,.. while i < buf_len-160 (VAD.C:121); buf_len <= 160 reads past the buffer in the reference
-        // (int -> u32 compare) -- here: no frames.
-        u32 nfr = (do_vad && buf_len > SR_FRAME_LEN && buf_len <= U) ? (buf_len - SR_FRAME_LEN + SR_FRAME_MOV - 1) / SR_FRAME_MOV : 0;
-        const u32 nblk = nfr ? nfr + 1 : 0;                        // frame k = blocks k, k+1
-        const u32 vad_samples = 80u * nblk;                        // <= buf_len
 
-        // ---- noise_atap, VAD.C:22-71: from the first staged chunk when it fits, else straight from global ----------
-        const bool atap_staged = atap_on && n_len <= kVadChunk;
+        // ---- noise_atap, VAD.C:22-71, when the window does not fit the first chunk: straight from global ------------
         if (atap_on && !atap_staged) {
-            const u16 *g = pcm + ubase;
-            u32 s = 0;
-            for (u32 i = lane; i < n_len; i += 32) s += g[i];
-            const u32 mid = warp_sum(s) / n_len;
-            u32 max_sum = 0, abs_sum = 0;
-            for (u32 i = 0; i < n_len; i += 240u) {
-                u32 mx = 0, sm = 0;
-                for (u32 h = lane; h < 240u; h += 32) { const u32 x = g[i + h], a = x > mid ? x - mid : mid - x; mx = max(mx, a); sm += a; }
-                max_sum += warp_max(mx);
-                abs_sum += sm;
-            }
-            abs_sum = warp_sum(abs_sum) / (n_len / SR_FRAME_LEN);
-            max_sum /= (n_len / 240u);
-            at.mid_val = mid; at.n_thl = (u16)max_sum; at.s_thl = abs_sum * 11u / 10u; at.z_thl = 2;
+            u32 m, max_sum, abs_sum;
+            atap_stats(pcm + ubase, false, n_len, lane, m, max_sum, abs_sum);
+            abs_sum /= (n_len / SR_FRAME_LEN);                             // VAD.C:65
+            max_sum /= (n_len / 240u);                                     // VAD.C:66
+            at.mid_val = m; at.n_thl = (u16)max_sum; at.s_thl = abs_sum * 11u / 10u; at.z_thl = 2;
             if (lane == 0) atap[b] = at;
         }
         u32 mid = at.mid_val, a_thl = mid + at.n_thl, b_thl = mid - at.n_thl;            // VAD.C:112-113 (u32 wrap)
 
-        // ---- stream the utterance in chunks of 32 blocks: one block per lane, every PCM byte read from HBM once ------
-        const u32 total = max(vad_samples, atap_staged ? n_len : 0u);
-        for (u32 c0 = 0; c0 < total; c0 += kVadChunk) {
-            const u32 cnt = min(kVadChunk, total - c0);
-            const int shift = stage_chunk(buf, pcm, total_bytes, base_aligned, ubase + c0, cnt, &bars[warp], phase, lane);
+        for (u32 c0 = 0; c0 < total; c0 += kVadChunk, ++k) {
+            const bool odd = k & 1u;
+            unsigned char *buf = odd ? buf1 : buf0;
+            if (odd) { mbar_wait(&bars[warp][1], ph1 & 1u); ++ph1; } else { mbar_wait(&bars[warp][0], ph0 & 1u); ++ph0; }
+            {                                                                  // next chunk of the stream -> other buffer
+                u32 nb = b, nc0 = c0 + kVadChunk;
+                if (nc0 >= total) { nb = b + stride; nc0 = 0; }
+                if (nb < B)
+                    shift_nxt = chunk_issue(odd ? buf0 : buf1, pcm, total_bytes, base_aligned, (size_t)nb * U + nc0,
+                                            min(kVadChunk, total - nc0), &bars[warp][odd ? 0 : 1], lane);
+            }
+            const int shift = shift_cur;
             VadWarpView v;
             v.x = reinterpret_cast<const u16 *>(buf) + shift;
             v.vec_ok = (shift & 7) == 0;
             if (c0 == 0 && atap_staged) {
-                u32 s = 0;
-                for (u32 i = lane; i < n_len; i += 32) s += v.x[i];
-                const u32 m = warp_sum(s) / n_len;                             // VAD.C:41-45
-                u32 max_sum = 0, abs_sum = 0;
-                for (u32 i = 0; i < n_len; i += 240u) {                        // VAD.C:48-63
-                    u32 mx = 0, sm = 0;
-                    for (u32 h = lane; h < 240u; h += 32) { const u32 x = v.x[i + h], a = x > m ? x - m : m - x; mx = max(mx, a); sm += a; }
-                    max_sum += warp_max(mx);
-                    abs_sum += sm;
-                }
-                abs_sum = warp_sum(abs_sum) / (n_len / SR_FRAME_LEN);          // VAD.C:65
+                u32 m, max_sum, abs_sum;
+                atap_stats(v.x, v.vec_ok, n_len, lane, m, max_sum, abs_sum);   // VAD.C:41-63
+                abs_sum /= (n_len / SR_FRAME_LEN);                             // VAD.C:65
                 max_sum /= (n_len / 240u);                                     // VAD.C:66
                 at.mid_val = m;
                 at.n_thl = (u16)max_sum;                                       // n_thl_ratio 1, VAD.C:68
@@ -235,13 +355,23 @@ vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, in
                 if (lane == 0) atap[b] = at;
                 mid = m; a_thl = mid + at.n_thl; b_thl = mid - at.n_thl;
             }
-            const u32 blk = c0 / 80u + (u32)lane;
-            if (blk < nblk) {
+            const u32 blk0 = c0 / 80u;
+            const u32 left = nblk > blk0 ? nblk - blk0 : 0u;                   // blocks of this chunk
+            if (left <= 4u && (shift & 1) == 0) {                              // few blocks: eight lanes per block
+                if (left) {
+                    u32 bs, fl;
+                    block_scan_split8(v.x, lane, left, mid, a_thl, b_thl, bs, fl);
+                    const u32 blk = blk0 + (u32)(lane >> 3);
+                    if ((lane & 7) == 0 && blk < nblk) { info[2 * blk] = bs; info[2 * blk + 1] = fl; }
+                }
+            } else if ((u32)lane < left) {
+                const u32 blk = blk0 + (u32)lane;
                 u32 bs, fl;
                 block_scan(v, 80u * (u32)lane, mid, a_thl, b_thl, bs, fl);
                 info[2 * blk] = bs; info[2 * blk + 1] = fl;
             }
-            __syncwarp();                                                      // buffer is re-staged next iteration
+            __syncwarp();                                                      // this buffer is re-staged one chunk later
+            shift_cur = shift_nxt;
         }
 
         // ---- VAD, VAD.C:97-218: frames from the block summaries ---------------------------------------------------
@@ -315,9 +445,9 @@ vad_kernel(const u16 *__restrict__ pcm, u32 U, u32 B, u32 n_len, u32 buf_len, in
 cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad,
                        atap_tag *atap, u32 *seg_off, int num_sms, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
-    const u32 buf_bytes = ((kVadChunk * 2 + 32 + 127) / 128) * 128;   // one 32-block chunk + alignment slack
+    const u32 buf_bytes = kVadChunk * 2 + 32;                          // one 32-block chunk + alignment slack (16-byte multiple)
     const u32 max_frames = 2 * ((buf_len > 160 ? (buf_len - 160 + 79) / 80 : 0) + 2);   // 2 words per 80-sample block
-    const size_t per_warp = (size_t)buf_bytes + (size_t)max_frames * 4;
+    const size_t per_warp = 2 * (size_t)buf_bytes + (size_t)max_frames * 4;   // two chunk buffers + block summaries
     int warps = (int)((220 * 1024) / per_warp);
     if (warps < 1) return cudaErrorInvalidValue;
     if (warps > kVadMaxWarps) warps = kVadMaxWarps;
