@@ -330,6 +330,11 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                 u32 te[8], to[8];
                 { const uint4 a = te4[0], c = te4[1]; te[0] = a.x; te[1] = a.y; te[2] = a.z; te[3] = a.w; te[4] = c.x; te[5] = c.y; te[6] = c.z; te[7] = c.w; }
                 { const uint4 a = to4[0], c = to4[1]; to[0] = a.x; to[1] = a.y; to[2] = a.z; to[3] = a.w; to[4] = c.x; to[5] = c.y; to[6] = c.z; to[7] = c.w; }
+                // running totals; the part below the lane's filter boundary is the total captured at i + 1 == split.
+                // (the empty asm keeps the 32 frame-invariant compares from being hoisted out of the frame loop, where
+                // ptxas would pack them into a bit mask that costs ~100 instructions per frame to rebuild and unpack)
+                int spe = sp_e, spo = sp_o;
+                asm volatile("" : "+r"(spe), "+r"(spo));
                 u32 s0e = 0, tote = 0, s0o = 0, toto = 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -337,8 +342,8 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                     const u32 wo = (i & 1) ? (to[i >> 1] >> 16) : (to[i >> 1] & 0xFFFFu);
                     const u32 ve = (E[i] * we) / 100u, vo = (E[i] * wo) / 100u;
                     tote += ve; toto += vo;
-                    if (i < sp_e) s0e += ve;
-                    if (i < sp_o) s0o += vo;
+                    if (i + 1 == spe) s0e = tote;
+                    if (i + 1 == spo) s0o = toto;
                 }
                 *reinterpret_cast<uint2 *>(&sm.seq[warp][0][2 * lane]) = make_uint2(s0e, tote - s0e);
                 *reinterpret_cast<uint2 *>(&sm.seq[warp][1][2 * lane]) = make_uint2(s0o, toto - s0o);

@@ -225,6 +225,34 @@ def test_vad_and_mfcc_fuzz_with_arbitrary_atap(handle, ora):
     assert ob.ftr_equal(handle.mfcc(pcm, sg, atap), ora.mfcc_batch(pcm, sg, atap))
 
 
+def test_vad_threshold_corner_cases(handle, ora):
+    """band edges at the corners of the packed 16-bit compare path: a_thl == 0, a_thl > 0xFFFF, b_thl == 0, b_thl wrapped
+    (VAD.C:112-113 are u32), mid_val beyond the sample range, thresholds equal to sample values; full-range u16 samples"""
+    rng = np.random.default_rng(2024)
+    combos = [(0, 0), (0, 1), (1, 1), (5, 5), (5, 6), (100, 100), (2048, 0), (2048, 2048), (2048, 2049), (65535, 0),
+              (65535, 1), (65000, 535), (65000, 536), (65000, 2000), (65535, 65535), (30000, 30000), (30000, 40000),
+              (65536, 1), (65536, 65535), (70000, 5000), (70000, 4464), (70000, 4465), (2 ** 32 - 5, 10), (2 ** 32 - 1, 0),
+              (2 ** 32 - 1, 1), (2 ** 31, 65535), (1, 0), (1, 2), (32768, 32768), (32768, 32767)]
+    B, U = len(combos) * 3, 4000
+    pcm = np.zeros((B, U), np.uint16)
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    for i, (mid, n) in enumerate(combos * 3):
+        kind = i // len(combos)
+        centre = min(mid, 65535)
+        if kind == 0:
+            pcm[i] = rng.integers(0, 65536, U)
+        elif kind == 1:                                  # hover around the band edges so >=, < and == all occur
+            pcm[i] = np.clip(centre + rng.integers(-3, 4, U) + rng.choice([-n, 0, n], U), 0, 65535)
+        else:                                            # sparse excursions: long in-band runs between markers
+            pcm[i] = centre
+            idx = rng.integers(0, U, 120)
+            pcm[i, idx] = rng.choice([0, 65535, max(centre - n, 0), min(centre + n, 65535), max(centre - n - 1, 0)], 120)
+        atap[i] = (mid, n, int(rng.integers(0, 6)), int(rng.integers(0, 400000)))
+    seg = handle.vad(pcm, atap)
+    for b in range(B):
+        assert ora.vad(pcm[b], U, atap[b:b + 1]).tolist() == seg[b].reshape(-1).tolist(), (b, combos[b % len(combos)])
+
+
 def test_dtw_limit_batch_and_drop_in_symbol(handle, ora):
     """dtw_limit (DTW.C:76-109): every lattice point of a few (I, M) shapes, and the reference-named symbol after dtw()"""
     L = sr_b200.lib()
