@@ -189,6 +189,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 
     // ================================ consumer warps ============================================
     u32 *fb = sm.fftbuf[warp];
+    const u32 fb_s = smem_u32(fb);
     s32 *wq = sm.wq[warp];
     const int q1 = lane & 3;
     // stage-1 twiddles (table block N=16, triple q1: legs K2 -> p2, K1 -> p1; leg 3 is all-zero)
@@ -272,7 +273,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                     cxadda4<14>(vr[0][m1], vi[0][m1], Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
                     const int e0 = 64 * G + q2;
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) fb[padF(e0 + 16 * m)] = pack16(o[2 * m], o[2 * m + 1]);
+                    for (int m = 0; m < 4; ++m) fb[padF(e0 + 16 * m)] = pack16(o[2 * m], o[2 * m + 1]);   // (two 16-bit stores measured slower)
                 }
             }
             __syncwarp();
@@ -286,15 +287,21 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                 const int2 k3 = k[0], k2 = k[1], k1 = k[2];
 #pragma unroll
                 for (int m4 = 0; m4 < 4; ++m4) {
-                    u32 p[4];
+                    // the packed points are read back as two sign-extending 16-bit loads each (LSU pipe) instead of one
+                    // 32-bit load + PRMT + SHF (ALU pipe): the ALU pipe is the scarce one
+                    u32 pr[4], pi[4];
 #pragma unroll
-                    for (int m3 = 0; m3 < 4; ++m3) p[m3] = fb[padF(256 * m4 + q3 + 64 * m3)];
+                    for (int m3 = 0; m3 < 4; ++m3) {
+                        const u32 a = fb_s + 4u * (u32)padF(256 * m4 + q3 + 64 * m3);
+                        // (asm: the compiler would fuse the pair back into one 32-bit load + extraction)
+                        asm volatile("ld.shared.s16 %0, [%2];\n ld.shared.s16 %1, [%2+2];" : "=r"(pr[m3]), "=r"(pi[m3]) : "r"(a) : "memory");
+                    }
                     u32 Dr, Di, Cr, Ci, Br, Bi;
-                    cxmul(Dr, Di, lo16s(p[3]), hi16s(p[3]), (u32)k3.x, (u32)k3.y);
-                    cxmul(Cr, Ci, lo16s(p[2]), hi16s(p[2]), (u32)k2.x, (u32)k2.y);
-                    cxmul(Br, Bi, lo16s(p[1]), hi16s(p[1]), (u32)k1.x, (u32)k1.y);
+                    cxmul(Dr, Di, pr[3], pi[3], (u32)k3.x, (u32)k3.y);
+                    cxmul(Cr, Ci, pr[2], pi[2], (u32)k2.x, (u32)k2.y);
+                    cxmul(Br, Bi, pr[1], pi[1], (u32)k1.x, (u32)k1.y);
                     u32 o[8];
-                    cxadda4<14>(lo16s(p[0]), hi16s(p[0]), Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                    cxadda4<14>(pr[0], pi[0], Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
 #pragma unroll
                     for (int m3 = 0; m3 < 4; ++m3) { vr[m4][m3] = o[2 * m3]; vi[m4][m3] = o[2 * m3 + 1]; }
                 }
