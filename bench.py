@@ -537,7 +537,7 @@ def main():
                 "other_kernels": other,
                 "algorithmic_bytes_per_launch": mfcc_bytes, "kernel_ms": kern_ms.get("mfcc"),
                 "kernel_share_of_step": share.get("mfcc"),
-                "note": "bit-exact fixed-point FFT: ~2000 warp instructions/frame -> INT-issue bound by design, see DESIGN.md"}
+                "note": "bit-exact fixed-point FFT: ~1850 warp instructions/frame -> INT-issue bound by design (see int_issue and DESIGN.md)"}
 
     # ---- CPU baseline on a bounded sample + parity of the GPU results on that sample ----------------------
     cpu = None
@@ -569,7 +569,7 @@ def main():
             iach = wipf * frames_rank0 / (kern_ms["mfcc"] * 1e-3)
             roofline["int_issue"] = {"achieved": iach / 1e9, "peak": ipeak / 1e9, "unit": "G warp-inst/s", "frac": iach / ipeak,
                                      "warp_inst_per_frame": wipf,
-                                     "note": "ALU and FMA-heavy (IMAD) pipes are half rate: both sit at ~65 % (profiles/)"}
+                                     "note": "ALU and FMA-heavy (IMAD) pipes are half rate; ncu: issue slots 81 % busy, FMA-heavy 74 %, ALU 58 % (profiles/r1_v6_full.md)"}
     except Exception:
         pass
 
