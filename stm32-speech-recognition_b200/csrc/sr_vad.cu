@@ -1,9 +1,9 @@
 // sr_vad.cu -- K0: batched noise_atap (Src/Speech_Recog/VAD.C:22-71) and VAD (VAD.C:97-218).
 //
-// One warp per utterance. The utterance's PCM is staged once into shared memory by a 1-D bulk
-// async copy (TMA engine) and both functions run on the staged copy, so HBM traffic is the
-// algorithmic 2*U bytes per utterance.
-//   * noise_atap: lane-strided sums / maxima + warp reductions;
+// One warp per utterance, persistent grid. A warp's utterances form one stream of 32-block chunks (2560 samples)
+// through two shared-memory buffers: 1-D bulk async copies (TMA engine) keep the next chunk in flight while the
+// current one is scanned, so HBM traffic is the algorithmic 2*U bytes per utterance.
+//   * noise_atap: from the first staged chunk, three lanes per 240-sample block (IDP.2A sums, 16-byte loads);
 //   * VAD features: frames overlap by 50 %, so the scan works on 80-sample BLOCKS (each sample is
 //     touched once) and frame k = block k + block k+1. A block summary is a small monoid element:
 //     sum |x-mid|, number of class alternations among its out-of-band samples, class of the last
