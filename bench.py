@@ -495,6 +495,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
     e2e_equal = bool(torch.equal(o_cmd.to(dev), cmd) and torch.equal(o_dis.to(dev), bdis))
+    tr_packed, tr_plain, tr_bytes = he.transport_stats()    # of the last step: chunks sent 12-bit packed / plain, bytes copied
     he.close()
 
     if rank != 0:
@@ -588,7 +589,8 @@ def main():
         "vad_ok_fraction": ok_total / total_utts,
         "kernel_ms": kern_ms, "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu_sample": parity,
         "e2e": {"value": total_utts / (e2e_ms * 1e-3), "unit": "utterances/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": B * U * 2, "d2h_bytes_per_step": B * 13, "matches_device_path": e2e_equal,
+                "h2d_bytes_per_step": tr_bytes if tr_bytes else B * U * 2, "d2h_bytes_per_step": B * 13, "matches_device_path": e2e_equal,
+                "transport": {"chunks_packed_12bit": tr_packed, "chunks_plain_u16": tr_plain, "host_pcm_bytes_per_step": B * U * 2},
                 "call": "sr_recognise_batch (host pinned buffers)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -214,6 +214,18 @@ int sr_fft_raw_batch(sr_handle *h, const uint32_t *in_packed, uint32_t n, uint32
  * from the IEEE sqrt.rn.f32 (0 over [1.0f, 2^33), the range the path can produce) */
 int sr_debug_sqrt_mismatches(sr_handle *h, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches);
 
+/* Packed PCM transport of sr_recognise_batch (host buffers): chunks whose samples are all < 4096 (the reference's
+ * 12-bit ADC range) may cross PCIe as 12 bits per sample, packed by host worker threads and expanded on the
+ * device; chunks with any larger sample travel as plain u16, so results never change. mode: 0 off, 1 on,
+ * -1 automatic (on when the process may use >= 8 CPUs; the default, also settable with SR_PACK12=0|1). */
+int sr_set_transport(sr_handle *h, int mode);
+/* transport statistics of the last sr_recognise_batch call: chunks sent packed / plain, bytes copied host -> device */
+int sr_transport_stats(const sr_handle *h, uint32_t *packed_chunks, uint32_t *plain_chunks, uint64_t *h2d_bytes);
+/* test hooks: the host packer alone (variant 0 scalar, 1 AVX2, 2 AVX-512 VBMI, -1 best available, 100+N the N-thread worker pool; returns the OR
+ * of all samples or 0xFFFFFFFF if the variant is unavailable; no GPU needed) and the device expander alone */
+uint32_t sr_debug_pack12_host(int variant, const uint16_t *src, uint64_t n, uint8_t *dst);
+int sr_debug_unpack12(sr_handle *h, const uint8_t *packed, uint64_t n, uint16_t *out);
+
 /* Per-kernel device timing: after sr_timing_enable(h, max_records) every kernel launch of this handle is
  * bracketed by a CUDA event pair on the launching stream; sr_timing_collect synchronises the stream and
  * returns (tag, milliseconds) per launch in issue order, then rearms. Tags: 0 noise_atap+VAD, 1 get_mfcc,

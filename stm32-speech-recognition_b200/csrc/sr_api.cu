@@ -3,6 +3,14 @@
 // recognition path happens on the host: every result is produced by the kernels in sr_vad.cu,
 // sr_mfcc.cu and sr_dtw.cu. Without a CUDA device every entry point fails loudly.
 #include "sr_internal.h"
+#include <condition_variable>
+#include <deque>
+#include <utility>
+#include "sr_pack_host.h"
+
+#ifndef SR_TRANSPORT_AUTO_DEFAULT
+#define SR_TRANSPORT_AUTO_DEFAULT 0      // what mode -1 (automatic) means: 1 = pack when >= 8 CPUs are usable
+#endif
 
 extern "C" {
 
@@ -56,7 +64,9 @@ int sr_destroy(sr_handle *h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
+    delete h->pool;
+    for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
+    DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
                       &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -325,6 +335,50 @@ int sr_dtw_batch(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, 
     return 0;
 }
 
+static bool transport_enabled(const sr_handle *h) {
+    int mode = h->transport_mode;
+    if (mode < 0) {
+        static const int env_mode = [] { const char *e = getenv("SR_PACK12"); return e && *e ? atoi(e) : -1; }();
+        mode = env_mode;
+    }
+    if (mode < 0) mode = SR_TRANSPORT_AUTO_DEFAULT && usable_cpus() >= 8 ? 1 : 0;
+    return mode > 0;
+}
+
+int sr_set_transport(sr_handle *h, int mode) {
+    SR_REQUIRE(h, h && mode >= -1 && mode <= 1);
+    h->transport_mode = mode;
+    return 0;
+}
+
+int sr_transport_stats(const sr_handle *h, uint32_t *packed_chunks, uint32_t *plain_chunks, uint64_t *h2d_bytes) {
+    if (!h) return -1;
+    if (packed_chunks) *packed_chunks = h->last_packed;
+    if (plain_chunks) *plain_chunks = h->last_plain;
+    if (h2d_bytes) *h2d_bytes = h->last_h2d;
+    return 0;
+}
+
+uint32_t sr_debug_pack12_host(int variant, const uint16_t *src, uint64_t n, uint8_t *dst) {
+    if (!src || !dst || (n & 1)) return 0xFFFFFFFFu;
+    if (variant >= 100) { PackPool pool(variant - 100); uint32_t o = 0; for (int rep = 0; rep < 3; ++rep) o = pool.run(src, (size_t)n, dst); return o; }   // the worker pool (3 fork-joins)
+    return variant < 0 ? pack12(src, (size_t)n, dst) : pack12_variant(variant, src, (size_t)n, dst);
+}
+
+int sr_debug_unpack12(sr_handle *h, const uint8_t *packed, uint64_t n, uint16_t *out) {
+    SR_REQUIRE(h, h && packed && out && !(n & 1));
+    if (n == 0) return 0;
+    DeviceGuard g(h->device);
+    SR_CK(h, ensure(h->misc0, (size_t)(n / 2 * 3) + 64));
+    SR_CK(h, ensure(h->misc1, (size_t)n * 2 + 64));
+    H2D(h, h->misc0.p, packed, (size_t)(n / 2 * 3));
+    SR_CK(h, launch_unpack12(h->misc0.p, n, static_cast<u16 *>(h->misc1.p), h->stream));
+    ++h->launches;
+    D2H(h, out, h->misc1.p, (size_t)n * 2);
+    SR_CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // Host-buffer spch_recg for B utterances. Large batches are processed in chunks through two device PCM
 // buffers: the H2D copy of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream), so
 // with pinned host memory the call is bound by max(PCIe, compute) instead of their sum.
@@ -353,16 +407,28 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     if (o->best_dis) { SR_CK(h, ensure(h->bdis, (size_t)B * 4)); d.best_dis = static_cast<u32 *>(h->bdis.p); }
     if (o->cmd) { SR_CK(h, ensure(h->cmd, (size_t)B * 4)); d.cmd = static_cast<u32 *>(h->cmd.p); }
     if (o->status) { SR_CK(h, ensure(h->status, (size_t)B)); d.status = static_cast<u8 *>(h->status.p); }
-    for (uint32_t c = 0; c < nchunks; ++c) {
+    // one chunk: H2D (plain u16, or 12-bit packed from a pinned staging slot + expansion on the device) -> kernels
+    auto issue_chunk = [&](uint32_t c, int buf, const void *packed_src) -> int {
         const uint32_t b0 = c * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
-        const int buf = (int)(c & 1);
+        const size_t ns = (size_t)nb * U;
         u16 *dpcm = reinterpret_cast<u16 *>(static_cast<unsigned char *>(h->pcm.p) + (size_t)buf * chunk_bytes);
         cudaStream_t cs = nchunks > 1 ? h->copy_stream : h->stream;
-        if (nchunks > 1 && c >= 2) SR_CK(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));      // buffer free again
-        SR_CK(h, cudaMemcpyAsync(dpcm, pcm + (size_t)b0 * U, (size_t)nb * U * 2, cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1 && h->chunk_seq >= 2) SR_CK(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));      // buffers free again
+        if (packed_src) {
+            unsigned char *dpk = static_cast<unsigned char *>(h->dpacked.p) + (size_t)buf * h->stage_cap;
+            SR_CK(h, cudaMemcpyAsync(dpk, packed_src, ns / 2 * 3, cudaMemcpyHostToDevice, cs));
+            h->last_h2d += ns / 2 * 3; ++h->last_packed;
+        } else {
+            SR_CK(h, cudaMemcpyAsync(dpcm, pcm + (size_t)b0 * U, ns * 2, cudaMemcpyHostToDevice, cs));
+            h->last_h2d += ns * 2; ++h->last_plain;
+        }
         if (nchunks > 1) {
             SR_CK(h, cudaEventRecord(h->ev_h2d[buf], cs));
             SR_CK(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[buf], 0));
+        }
+        if (packed_src) {
+            SR_CK(h, launch_unpack12(static_cast<unsigned char *>(h->dpacked.p) + (size_t)buf * h->stage_cap, ns, dpcm, h->stream));
+            ++h->launches;
         }
         sr_recog_out dc = d;
         if (d.atap) dc.atap = d.atap + b0;
@@ -376,6 +442,102 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         int rc = sr_recognise_batch_dev(h, dpcm, U, nb, n_len, &dc);
         if (rc) return rc;
         if (nchunks > 1) SR_CK(h, cudaEventRecord(h->ev_done[buf], h->stream));
+        ++h->chunk_seq;
+        return 0;
+    };
+    h->chunk_seq = 0; h->last_packed = 0; h->last_plain = 0; h->last_h2d = 0;
+
+    bool packed_transport = nchunks >= 4 && transport_enabled(h);
+    if (packed_transport) {                              // workers, pinned staging slots, device staging
+        const size_t pk = ((((size_t)chunk * U + 1) / 2 * 3 + 64 + 255) / 256) * 256;
+        if (!h->pool) {
+            int nt = usable_cpus() - 2;
+            nt = nt > 16 ? 16 : nt;
+            if (nt >= 2) h->pool = new (std::nothrow) PackPool(nt);
+        }
+        if (h->pool && h->stage_cap < pk) {
+            for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
+            h->stage_cap = 0;
+            bool ok = true;
+            for (void *&st : h->stage) if (ok && cudaHostAlloc(&st, pk, cudaHostAllocDefault) != cudaSuccess) { st = nullptr; ok = false; }
+            if (ok) h->stage_cap = pk;
+            else { cudaGetLastError(); for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; } }
+        }
+        if (!h->pool || !h->stage_cap || ensure(h->dpacked, 2 * h->stage_cap) != cudaSuccess) { cudaGetLastError(); packed_transport = false; }
+    }
+
+    if (!packed_transport) {
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            int rc = issue_chunk(c, (int)(c & 1), nullptr);
+            if (rc) return rc;
+        }
+    } else {
+        // The caller's thread sends chunks from the front as plain u16, paced by the copy engine; the worker pool packs
+        // chunks from the back into the staging slots and those are sent packed as soon as they are ready. The two
+        // meet in the middle, so the call is never slower than the plain path and approaches 3/4 of its PCIe time.
+        std::mutex m;
+        std::condition_variable cv_slot;
+        std::deque<std::pair<uint32_t, int>> ready;       // (chunk, staging slot)
+        std::vector<uint32_t> retry;                      // chunks that hold a sample >= 4096: sent plain
+        int lo = 0, hi = (int)nchunks - 1;                // unclaimed chunks [lo, hi]
+        unsigned free_mask = (1u << sr_handle::kStage) - 1u;
+        bool abort = false;
+        std::thread packer([&] {
+            for (;;) {
+                int slot;
+                uint32_t c;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv_slot.wait(lk, [&] { return abort || lo > hi || free_mask != 0; });
+                    if (abort || lo > hi) return;
+                    slot = __builtin_ctz(free_mask);
+                    free_mask &= ~(1u << slot);
+                    c = (uint32_t)hi--;
+                }
+                const uint32_t b0 = c * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
+                const size_t ns = (size_t)nb * U;
+                const uint32_t orb = (ns & 1) ? 0xFFFFu : h->pool->run(pcm + (size_t)b0 * U, ns, static_cast<uint8_t *>(h->stage[slot]));
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    if (orb & 0xF000u) { retry.push_back(c); free_mask |= 1u << slot; }
+                    else ready.emplace_back(c, slot);
+                }
+            }
+        });
+        int rc = 0;
+        int slot_of[2] = {-1, -1};                        // staging slot behind the copy last issued on each buffer
+        auto release = [&](int &sl) {
+            if (sl < 0) return;
+            { std::lock_guard<std::mutex> lk(m); free_mask |= 1u << sl; }
+            cv_slot.notify_one();
+            sl = -1;
+        };
+        uint32_t sent = 0;
+        while (sent < nchunks) {
+            int slot = -1;
+            long c = -1;
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (!ready.empty()) { c = ready.front().first; slot = ready.front().second; ready.pop_front(); }
+                else if (!retry.empty()) { c = retry.back(); retry.pop_back(); }
+                else if (lo <= hi) c = lo++;
+            }
+            if (c < 0) { std::this_thread::yield(); continue; }          // every chunk is claimed; the pool is still packing
+            const int buf = (int)(sent & 1);
+            if (sent >= 2) {                                               // at most two copies in flight: paces this thread
+                cudaError_t e = cudaEventSynchronize(h->ev_h2d[buf]);
+                if (e != cudaSuccess) { rc = fail(h, "cudaEventSynchronize", e); if (slot >= 0) release(slot); break; }
+                release(slot_of[buf]);
+            }
+            rc = issue_chunk((uint32_t)c, buf, slot >= 0 ? h->stage[slot] : nullptr);
+            if (rc) { if (slot >= 0) release(slot); break; }
+            slot_of[buf] = slot;
+            ++sent;
+        }
+        { std::lock_guard<std::mutex> lk(m); abort = true; }
+        cv_slot.notify_all();
+        packer.join();
+        if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
     }
     if (o->atap) D2H(h, o->atap, d.atap, (size_t)B * sizeof(atap_tag));
     if (o->seg_off) D2H(h, o->seg_off, d.seg_off, (size_t)B * 24);

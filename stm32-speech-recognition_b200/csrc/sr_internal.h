@@ -31,6 +31,8 @@ cudaError_t launch_dtw_limit(const u16 *x, const u16 *y, const u16 *I, const u16
 cudaError_t launch_get_mdl(const void *in1, const void *in2, void *mdl, u32 n, u32 *dis, cudaStream_t st);
 cudaError_t launch_pack_slots(const void *ftr, const u8 *status, u32 B, void *bank, u32 slot_stride, cudaStream_t st);
 cudaError_t launch_sqrt_check(u32 lo, u32 hi, unsigned long long *bad_dev, cudaStream_t st);
+cudaError_t launch_unpack12(const void *packed, u64 n_samples, u16 *out, cudaStream_t st);
+class PackPool;
 }  // namespace srk
 
 using namespace srk;
@@ -60,6 +62,15 @@ struct sr_handle {
     std::vector<cudaEvent_t> ev;
     std::vector<uint32_t> ev_tag;
     size_t ev_used = 0;
+    // packed PCM transport (sr_recognise_batch): worker pool, pinned staging slots, device staging
+    int transport_mode = -1;                            // 0 off, 1 on, -1 automatic
+    PackPool *pool = nullptr;
+    static constexpr int kStage = 4;
+    void *stage[kStage] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_cap = 0;
+    uint32_t last_packed = 0, last_plain = 0, chunk_seq = 0;
+    uint64_t last_h2d = 0;
+    DevBuf dpacked;
     // grow-only device workspaces
     DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
 };

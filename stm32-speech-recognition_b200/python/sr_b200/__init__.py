@@ -64,6 +64,11 @@ def lib():
         L.sr_timing_enable.argtypes = [vp, u32]
         L.sr_timing_collect.argtypes = [vp, vp, vp, u32, vp]
         L.sr_debug_sqrt_mismatches.argtypes = [vp, u32, u32, vp]
+        L.sr_set_transport.argtypes = [vp, C.c_int]
+        L.sr_transport_stats.argtypes = [vp, vp, vp, vp]
+        L.sr_debug_pack12_host.argtypes = [C.c_int, vp, u64, vp]
+        L.sr_debug_pack12_host.restype = u32
+        L.sr_debug_unpack12.argtypes = [vp, vp, u64, vp]
         L.sr_enrol_batch.argtypes = [vp, vp, u32, u32, u32, vp, u32, vp]
         L.sr_get_mdl_batch.argtypes = [vp, vp, vp, u32, vp, vp]
         L.sr_streams_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp)]
@@ -162,6 +167,23 @@ class Handle:
 
     def launch_count(self):
         return int(lib().sr_launch_count(self._h))
+
+    def set_transport(self, mode):
+        """packed PCM transport of sr_recognise_batch: 0 off, 1 on, -1 automatic"""
+        self._ck(lib().sr_set_transport(self._h, int(mode)))
+
+    def transport_stats(self):
+        """(packed chunks, plain chunks, bytes copied host -> device) of the last recognise() call on host buffers"""
+        a, b, c = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        lib().sr_transport_stats(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return int(a.value), int(b.value), int(c.value)
+
+    def unpack12(self, packed, n):
+        """device expander of the packed transport alone (test hook): n samples from n/2*3 bytes"""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        out = np.empty(n, np.uint16)
+        self._ck(lib().sr_debug_unpack12(self._h, _p(packed.ctypes.data), n, _p(out.ctypes.data)))
+        return out
 
     def timing_enable(self, max_records):
         self._ck(lib().sr_timing_enable(self._h, max_records))
@@ -391,3 +413,12 @@ def make_bank(ftr, slot_stride=4096, valid=None):
         bank[t, 0] = sign & 0xFF
         bank[t, 1] = sign >> 8
     return bank
+
+
+def pack12_host(x, variant=-1):
+    """host packer of the packed transport alone (test hook, no GPU): returns (packed bytes, OR of all samples) or None if
+    the variant is not available on this CPU"""
+    x = np.ascontiguousarray(x, np.uint16)
+    dst = np.zeros(x.size // 2 * 3, np.uint8)
+    o = lib().sr_debug_pack12_host(int(variant), _p(x.ctypes.data), x.size, _p(dst.ctypes.data))
+    return None if o == 0xFFFFFFFF else (dst, int(o))

@@ -588,6 +588,44 @@ def test_thin_c_host_links_reference_named_symbols():
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:]
 
 
+def test_unpack12_device_expander(handle):
+    rng = np.random.default_rng(12)
+    for n in [2, 14, 16, 18, 4098, 1000002]:
+        x = rng.integers(0, 4096, n).astype(np.uint16)
+        packed, orbits = sr_b200.pack12_host(x)
+        assert (orbits & 0xF000) == 0
+        assert np.array_equal(handle.unpack12(packed, n), x), n
+
+
+def test_packed_transport_equals_plain(handle, ora):
+    """sr_recognise_batch with the 12-bit packed PCIe transport: same results as the plain transport, chunks holding a sample
+    >= 4096 travel plain, and both agree with the oracle on a sample"""
+    B, U, T = 9000, 8000, 7                             # 5 chunks of 2096 utterances (32 MB)
+    pcm = sr_b200.synth_pcm_host(B, U, 0x7A000000)
+    pcm[2500, 17] = 4096                                # chunks 1 and 4 cannot be packed
+    pcm[8999, 7999] = 65535
+    handle.set_bank(np.zeros((1, 4096), np.uint8), 0, 4096)
+    e = handle.recognise(sr_b200.synth_pcm_host(T, U, 0x7E3A0000), 2400, want=("ftr", "status"))
+    bank = sr_b200.make_bank(e["ftr"])
+    handle.set_bank(bank, T, 4096)
+    try:
+        handle.set_transport(0)
+        plain = handle.recognise(pcm, 2400)
+        assert handle.transport_stats()[0] == 0
+        handle.set_transport(1)
+        packed = handle.recognise(pcm, 2400)
+        n_packed, n_plain, nbytes = handle.transport_stats()
+    finally:
+        handle.set_transport(-1)
+    assert n_packed + n_plain == 5 and n_plain >= 2 and n_packed >= 1, (n_packed, n_plain)
+    assert nbytes < pcm.nbytes
+    for k in plain:
+        assert plain[k].tobytes() == packed[k].tobytes(), k
+    sel = np.array([0, 2095, 2096, 2500, 4191, 4192, 8383, 8384, 8999])
+    ref = ora.recognise_batch(pcm[sel], 2400, bank, T, 4096)
+    _cmp_recog({k: v[sel] for k, v in packed.items()}, ref)
+
+
 def test_empty_batch_and_argument_errors(handle):
     z = np.zeros((0, 8000), np.uint16)
     assert handle.recognise(z, 2400)["cmd"].shape == (0,)
