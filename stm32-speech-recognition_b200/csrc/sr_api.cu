@@ -3,6 +3,7 @@
 // recognition path happens on the host: every result is produced by the kernels in sr_vad.cu,
 // sr_mfcc.cu and sr_dtw.cu. Without a CUDA device every entry point fails loudly.
 #include "sr_internal.h"
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <utility>
@@ -51,7 +52,7 @@ int sr_create(int device, sr_handle **out) {
     h->stream = h->own_stream;
     e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+        e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming | cudaEventBlockingSync);   // the packed transport's sender sleeps on it
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) { delete h; return fail(nullptr, "stream/event creation", e); }
@@ -451,7 +452,9 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     if (packed_transport) {                              // workers, pinned staging slots, device staging
         const size_t pk = ((((size_t)chunk * U + 1) / 2 * 3 + 64 + 255) / 256) * 256;
         if (!h->pool) {
-            int nt = usable_cpus() - 2;
+            // leave room under a cgroup CPU quota for the sender, the CUDA runtime's threads and the caller's own work
+            static const int env_nt = [] { const char *e = getenv("SR_PACK_THREADS"); return e && *e ? atoi(e) : 0; }();
+            int nt = env_nt > 0 ? env_nt : usable_cpus() - 4;
             nt = nt > 16 ? 16 : nt;
             if (nt >= 2) h->pool = new (std::nothrow) PackPool(nt);
         }
@@ -522,7 +525,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
                 else if (!retry.empty()) { c = retry.back(); retry.pop_back(); }
                 else if (lo <= hi) c = lo++;
             }
-            if (c < 0) { std::this_thread::yield(); continue; }          // every chunk is claimed; the pool is still packing
+            if (c < 0) { std::this_thread::sleep_for(std::chrono::microseconds(50)); continue; }   // every chunk is claimed; the pool is still packing
             const int buf = (int)(sent & 1);
             if (sent >= 2) {                                               // at most two copies in flight: paces this thread
                 cudaError_t e = cudaEventSynchronize(h->ev_h2d[buf]);
