@@ -221,7 +221,7 @@ int sr_debug_sqrt_mismatches(sr_handle *h, uint32_t lo_bits, uint32_t hi_bits, u
 int sr_set_transport(sr_handle *h, int mode);
 /* transport statistics of the last sr_recognise_batch call: chunks sent packed / plain, bytes copied host -> device */
 int sr_transport_stats(const sr_handle *h, uint32_t *packed_chunks, uint32_t *plain_chunks, uint64_t *h2d_bytes);
-/* test hooks: the host packer alone (variant 0 scalar, 1 AVX2, 2 AVX-512 VBMI, -1 best available, 100+N the N-thread worker pool; returns the OR
+/* test hooks: the host packer alone (variant 0 scalar, 1 AVX2, 2 AVX-512 VBMI, 3 AVX-512 VBMI with non-temporal stores, -1 best available, 100+N the N-thread worker pool; returns the OR
  * of all samples or 0xFFFFFFFF if the variant is unavailable; no GPU needed) and the device expander alone */
 uint32_t sr_debug_pack12_host(int variant, const uint16_t *src, uint64_t n, uint8_t *dst);
 int sr_debug_unpack12(sr_handle *h, const uint8_t *packed, uint64_t n, uint16_t *out);

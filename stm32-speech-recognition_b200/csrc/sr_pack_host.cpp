@@ -80,10 +80,46 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) static uint32_t pack12_vb
     return o | pack12_scalar(src + i, n - i, dst + (i >> 1) * 3);
 }
 
+// Same, 128 samples (three whole cache lines of output) per iteration with two-source byte permutes and NON-TEMPORAL
+// stores: the packed bytes go straight to memory without the read-for-ownership a normal store to a cold line costs
+// (2 B read + 1.5 B written per sample instead of 2 + 1.5 + 1.5). dst must be 64-byte aligned.
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) static uint32_t pack12_vbmi_nt(const uint16_t *src, size_t n,
+                                                                                      uint8_t *dst) {
+    if (reinterpret_cast<uintptr_t>(dst) & 63) return pack12_vbmi(src, n, dst);
+    alignas(64) uint8_t i0[64], i1[64], i2[64];
+    auto at = [](int k) { return (uint8_t)(4 * (k / 3) + k % 3); };          // packed byte k of a vector -> byte of the 24-in-32 layout
+    for (int j = 0; j < 64; ++j) {
+        i0[j] = j < 48 ? at(j) : (uint8_t)(64 + at(j - 48));                   // line 0: vector 0 bytes 0..47, vector 1 bytes 0..15
+        i1[j] = j < 32 ? at(16 + j) : (uint8_t)(64 + at(j - 32));              // line 1: vector 1 bytes 16..47, vector 2 bytes 0..31
+        i2[j] = j < 16 ? at(32 + j) : (uint8_t)(64 + at(j - 16));              // line 2: vector 2 bytes 32..47, vector 3 bytes 0..47
+    }
+    const __m512i x0 = _mm512_load_si512(i0), x1 = _mm512_load_si512(i1), x2 = _mm512_load_si512(i2);
+    const __m512i m1 = _mm512_set1_epi32(0x00000FFF), m2 = _mm512_set1_epi32(0x00FFF000);
+    __m512i acc = _mm512_setzero_si512();
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m512i v0 = _mm512_loadu_si512(src + i), v1 = _mm512_loadu_si512(src + i + 32),
+                      v2 = _mm512_loadu_si512(src + i + 64), v3 = _mm512_loadu_si512(src + i + 96);
+        acc = _mm512_or_si512(_mm512_or_si512(acc, _mm512_or_si512(v0, v1)), _mm512_or_si512(v2, v3));
+        const __m512i p0 = _mm512_or_si512(_mm512_and_si512(v0, m1), _mm512_and_si512(_mm512_srli_epi32(v0, 4), m2));
+        const __m512i p1 = _mm512_or_si512(_mm512_and_si512(v1, m1), _mm512_and_si512(_mm512_srli_epi32(v1, 4), m2));
+        const __m512i p2 = _mm512_or_si512(_mm512_and_si512(v2, m1), _mm512_and_si512(_mm512_srli_epi32(v2, 4), m2));
+        const __m512i p3 = _mm512_or_si512(_mm512_and_si512(v3, m1), _mm512_and_si512(_mm512_srli_epi32(v3, 4), m2));
+        uint8_t *d = dst + (i >> 1) * 3;
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(d), _mm512_permutex2var_epi8(p0, x0, p1));
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(d + 64), _mm512_permutex2var_epi8(p1, x1, p2));
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(d + 128), _mm512_permutex2var_epi8(p2, x2, p3));
+    }
+    _mm_sfence();
+    uint32_t o = (uint32_t)_mm512_reduce_or_epi32(acc);
+    o = (o | (o >> 16)) & 0xFFFFu;
+    return o | pack12_vbmi(src + i, n - i, dst + (i >> 1) * 3);
+}
+
 typedef uint32_t (*pack_fn)(const uint16_t *, size_t, uint8_t *);
 static pack_fn pick_pack() {
     __builtin_cpu_init();
-    if (__builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw")) return pack12_vbmi;
+    if (__builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw")) return pack12_vbmi_nt;
     if (__builtin_cpu_supports("avx2")) return pack12_avx2;
     return pack12_scalar;
 }
@@ -93,7 +129,9 @@ uint32_t pack12(const uint16_t *src, size_t n, uint8_t *dst) {
 }
 uint32_t pack12_variant(int variant, const uint16_t *src, size_t n, uint8_t *dst) {
     __builtin_cpu_init();
-    if (variant == 2 && __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw")) return pack12_vbmi(src, n, dst);
+    const bool vbmi = __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw");
+    if (variant == 3 && vbmi) return pack12_vbmi_nt(src, n, dst);
+    if (variant == 2 && vbmi) return pack12_vbmi(src, n, dst);
     if (variant == 1 && __builtin_cpu_supports("avx2")) return pack12_avx2(src, n, dst);
     if (variant == 0) return pack12_scalar(src, n, dst);
     return 0xFFFFFFFFu;   // variant not available on this CPU
@@ -133,12 +171,12 @@ struct PackPool::Impl {
     int nthreads = 0;
 
     void slice(int t) {
-        // slices are multiples of 32 samples (48 packed bytes): no two workers touch the same output byte
-        const size_t groups = n / 32, per = (groups + nthreads - 1) / nthreads;
+        // slices are multiples of 128 samples (192 packed bytes, three cache lines): no two workers touch the same line
+        const size_t groups = n / 128, per = (groups + nthreads - 1) / nthreads;
         const size_t g0 = (size_t)t * per, g1 = g0 + per < groups ? g0 + per : groups;
         uint32_t o = 0;
-        if (g0 < g1) o = pack12(src + g0 * 32, (g1 - g0) * 32, dst + g0 * 48);
-        if (t == nthreads - 1 && groups * 32 < n) o |= pack12(src + groups * 32, n - groups * 32, dst + groups * 48);
+        if (g0 < g1) o = pack12(src + g0 * 128, (g1 - g0) * 128, dst + g0 * 192);
+        if (t == nthreads - 1 && groups * 128 < n) o |= pack12(src + groups * 128, n - groups * 128, dst + groups * 192);
         orbits.fetch_or(o, std::memory_order_relaxed);
     }
     void worker(int t) {
