@@ -454,7 +454,9 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         if (!h->pool) {
             // leave room under a cgroup CPU quota for the sender, the CUDA runtime's threads and the caller's own work
             static const int env_nt = [] { const char *e = getenv("SR_PACK_THREADS"); return e && *e ? atoi(e) : 0; }();
-            int nt = env_nt > 0 ? env_nt : usable_cpus() - 4;
+            // under torchrun the ranks of one node share the CPU quota
+            static const int local_world = [] { const char *e = getenv("LOCAL_WORLD_SIZE"); const int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();
+            int nt = env_nt > 0 ? env_nt : usable_cpus() / local_world - 4;
             nt = nt > 16 ? 16 : nt;
             if (nt >= 2) h->pool = new (std::nothrow) PackPool(nt);
         }
@@ -462,7 +464,9 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
             for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
             h->stage_cap = 0;
             bool ok = true;
-            for (void *&st : h->stage) if (ok && cudaHostAlloc(&st, pk, cudaHostAllocDefault) != cudaSuccess) { st = nullptr; ok = false; }
+            // SR_PACK_WC=1: write-combined staging (the packers only ever stream whole cache lines into it and never read it back)
+            static const unsigned stage_flags = [] { const char *e = getenv("SR_PACK_WC"); return e && atoi(e) > 0 ? cudaHostAllocWriteCombined : cudaHostAllocDefault; }();
+            for (void *&st : h->stage) if (ok && cudaHostAlloc(&st, pk, stage_flags) != cudaSuccess) { st = nullptr; ok = false; }
             if (ok) h->stage_cap = pk;
             else { cudaGetLastError(); for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; } }
         }
