@@ -185,6 +185,19 @@ def test_vad_lengths(handle, ora, U, buf_len):
             assert (seg[b] == ob.NULL).all()
 
 
+def test_noise_atap_windows_longer_than_one_chunk(handle, ora):
+    """noise windows beyond the 2 560 samples the kernel stages per chunk take the direct global-memory path"""
+    B, U = 40, 16000
+    pcm = sr_b200.synth_pcm_host(B, U, 0x5150)
+    for n_len in (2640, 4800, 7200, 15840):
+        atap = handle.noise_atap(pcm, n_len)
+        seg = handle.vad(pcm, atap)
+        for b in range(B):
+            a = ora.noise_atap(pcm[b], n_len)
+            assert a.tobytes() == atap[b:b + 1].tobytes(), (n_len, b)
+            assert ora.vad(pcm[b], U, a).tolist() == seg[b].reshape(-1).tolist(), (n_len, b)
+
+
 def test_vad_and_mfcc_fuzz_with_arbitrary_atap(handle, ora):
     """random PCM shapes and ARBITRARY adaptive parameters handed straight to VAD / get_mfcc (n_thl > mid makes the lower
     band edge wrap, VAD.C:113; huge mid_val exercises the s32 casts of MFCC.C:110,119)"""
