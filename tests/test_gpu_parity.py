@@ -630,8 +630,15 @@ def test_packed_transport_equals_plain(handle, ora):
         n_packed, n_plain, nbytes = handle.transport_stats()
     finally:
         handle.set_transport(-1)
-    assert n_packed + n_plain == 5 and n_plain >= 2 and n_packed >= 1, (n_packed, n_plain)
-    assert nbytes < pcm.nbytes
+    assert n_packed + n_plain == 5 and n_plain >= 2, (n_packed, n_plain)
+    cpus = len(os.sched_getaffinity(0))
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        cpus = cpus if q == "max" else min(cpus, -(-int(q) // int(per)))
+    except (OSError, ValueError):
+        pass
+    if cpus >= 8:                                       # with fewer CPUs the library creates no packer pool: everything plain
+        assert n_packed >= 1 and nbytes < pcm.nbytes, (n_packed, n_plain, nbytes)
     for k in plain:
         assert plain[k].tobytes() == packed[k].tobytes(), k
     sel = np.array([0, 2095, 2096, 2500, 4191, 4192, 8383, 8384, 8999])
