@@ -106,7 +106,17 @@ const char *sr_last_error(const sr_handle *h /* NULL: last error of the calling 
 int         sr_device_count(void);                        /* 0 when no CUDA device is usable         */
 int         sr_abi_version(void);
 void       *sr_host_alloc(size_t bytes);                  /* pinned host memory for fast H2D/D2H     */
-void        sr_host_free(void *p);
+void        sr_host_free(void *p);                        /* for sr_host_alloc and sr_host_alloc_dev  */
+/* NUMA placement of the host side. The end-to-end call is bound by the H2D copy of the caller's PCM (the u16 v_dat
+ * buffer of main.c:249), so on a two-socket box the pinned pages and the threads that feed a GPU belong on the
+ * socket that GPU hangs off. sr_host_alloc_dev returns pinned memory whose pages live on `device`'s NUMA node
+ * (plain sr_host_alloc on single-node boxes); sr_bind_thread_to_device restricts the CALLING thread (and every
+ * thread it creates afterwards, e.g. the library's packer pool) to that node's CPUs and returns the node, or -1 when
+ * nothing was changed (one node, unknown topology); sr_device_numa_node / sr_host_numa_node report placement. */
+void       *sr_host_alloc_dev(int device, size_t bytes);
+int         sr_bind_thread_to_device(int device);
+int         sr_device_numa_node(int device);              /* -1 = unknown                            */
+int         sr_host_numa_node(const void *p);             /* node backing the page at p; -1 = unknown */
 
 /* Template bank: n_slot slots of slot_stride bytes (>= sizeof(v_ftr_tag), multiple of 4), each
  * starting with a v_ftr_tag; the flash layout of Flash.H:11-20 is slot_stride = 4096.
@@ -149,11 +159,39 @@ typedef struct {
 int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
                        const sr_recog_out *out);
 
+/* Command labels: commstr[] of main.c:25-31, the u8* spch_recg returns (main.c:295). n_labels records of label_stride
+ * bytes (the reference: comm_tag {u8 str[3]}), copied. Without a table the reference's own 18 labels are used
+ * ("0 ".."9 ", then the GBK codes of up/down/front/back/left/right/big/small). sr_label returns NULL for a command
+ * index without a label; sr_labels_batch maps the cmd/status arrays of sr_recognise_batch, NULL where spch_recg
+ * returns NULL (VAD or MFCC failed, main.c:261-274). */
+int            sr_set_labels(sr_handle *h, const void *labels, uint32_t n_labels, uint32_t label_stride);
+const uint8_t *sr_label(const sr_handle *h /* may be NULL: reference table */, uint32_t cmd);
+int            sr_labels_batch(const sr_handle *h, const uint32_t *cmd, const uint8_t *status, uint32_t B, const uint8_t **labels_out);
+
 /* The same call spread over several GPUs of one box: contiguous shards, one host thread per handle, results
  * written straight into the caller's host arrays (no collective needed for host outputs). handles[g] must be
  * handles on different devices with the same bank set. */
 int sr_recognise_batch_multi(sr_handle *const *handles, uint32_t n_handles, const uint16_t *pcm, uint32_t U, uint32_t B,
                              uint32_t n_len, const sr_recog_out *out);
+
+/* ---- the one exchange step of the multi-GPU form: NCCL all-gather behind the C-ABI ----------------------
+ * Utterances are sharded over ranks -- one handle per GPU, one process or one host thread per rank -- with no
+ * data-path communication; at the end the per-template scores (and the 8-byte argmin keys) of all shards are
+ * all-gathered. NCCL is bound at run time (dlopen of libnccl.so.2, SR_NCCL_LIB overrides), so single-GPU users need
+ * no NCCL at all. sr_comm_unique_id is called on ONE rank and its 128 bytes handed to the others by the host's own
+ * means (shared memory between threads, a file, MPI, torch.distributed ...); sr_comm_create is collective.
+ * The collective runs on a stream of its own, ordered after the kernels that produced its input, and overlaps whatever
+ * the handle's stream does next; sr_comm_wait makes the handle's stream (and thus sr_sync) wait for it. Errors:
+ * 10000 + ncclResult_t, or -2 when NCCL cannot be loaded. */
+#define SR_COMM_ID_BYTES 128
+int sr_comm_unique_id(void *id128);
+int sr_comm_create(sr_handle *h, int rank, int world, const void *id128);
+int sr_comm_destroy(sr_handle *h);
+int sr_comm_rank(const sr_handle *h);
+int sr_comm_world(const sr_handle *h);
+int sr_comm_nccl_version(void);                           /* 0 when NCCL cannot be loaded */
+int sr_comm_wait(sr_handle *h);
+int sr_allgather_dev(sr_handle *h, const void *send_dev, void *recv_dev, size_t bytes_per_rank);
 
 /* device-pointer variants: every pointer is device memory on the handle's device, calls are
  * asynchronous on the handle's stream. Alignment: pcm 2 bytes, everything else 4 bytes. */
@@ -166,6 +204,11 @@ int sr_dtw_batch_dev(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t fla
                      uint32_t *score, uint32_t *best_idx, uint32_t *best_dis);
 int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
                            const sr_recog_out *out_dev);
+/* sr_recognise_batch_dev on this rank's shard + the exchange step: gathered_score[world*B][n_slot] (rank-major, i.e.
+ * global utterance order for equal contiguous shards; needs out_dev->score) and/or gathered_best[world*B] =
+ * best_dis << 32 | best_idx, the key of the strict-'<' first-wins argmin (main.c:285-289). Either may be NULL. */
+int sr_recognise_batch_dev_allgather(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
+                                     const sr_recog_out *out_dev, uint32_t *gathered_score, uint64_t *gathered_best);
 
 /* save_mdl (main.c:121-138) for B utterances: noise_atap -> VAD -> get_mfcc(segment 0) -> save_ftr_mdl
  * (Flash.C:17-67) into slot b of a flash-layout bank image bank_out[B][slot_stride] (host memory).
@@ -179,11 +222,14 @@ int sr_enrol_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, ui
 int sr_get_mdl_batch(sr_handle *h, const v_ftr_tag *in1, const v_ftr_tag *in2, uint32_t n, v_ftr_tag *mdl, uint32_t *dis);
 
 /* ---- streaming front end (stands in for record(), main.c:77-102 / ADC.C:11-103) ----------------------------
- * n_streams concurrent captures of max_samples samples each, fed in lock-step chunks. Each push advances
- * noise_atap (once the first n_len samples are in) and VAD frame by frame with the reference's carried state,
- * and recognises every segment that closes (get_mfcc + dtw + argmin against the handle's bank). After the
- * last chunk the events equal the batch results on the complete buffers; the reference itself only ever
- * recognises segment 0 (main.c:268), here all <= 3 segments of a stream produce an event. */
+ * n_streams concurrent captures of max_samples samples each, fed in chunks -- in lock step (sr_streams_push) or every
+ * stream at its own pace (sr_streams_push_ragged). Each push advances noise_atap (once the first n_len samples of a
+ * stream are in) and VAD with the reference's carried state, and recognises every segment that closes (get_mfcc + dtw
+ * + argmin against the handle's bank): one H2D copy, five kernels, one D2H copy and ONE synchronisation per push.
+ * After the last chunk the events equal the batch results on the complete buffers; the reference itself only ever
+ * recognises segment 0 (main.c:268), here all <= 3 segments of a stream produce an event.
+ * Events are never dropped: what does not fit max_events stays queued (oldest first) and is handed out by the next
+ * push or by sr_streams_fetch; 3 * n_streams is always enough for one push. */
 typedef struct sr_stream_pool sr_stream_pool;
 typedef struct {
     uint32_t stream, segment;   /* which stream, which of its <= 3 segments       */
@@ -196,7 +242,26 @@ int sr_streams_destroy(sr_stream_pool *p);
 int sr_streams_reset(sr_stream_pool *p);
 int sr_streams_push(sr_stream_pool *p, const uint16_t *chunk /* host [n_streams][chunk_stride] */, uint32_t chunk_len,
                     uint32_t chunk_stride, sr_stream_event *events, uint32_t max_events, uint32_t *n_events);
+int sr_streams_push_ragged(sr_stream_pool *p, const uint16_t *chunk /* host [n_streams][chunk_stride] */, uint32_t chunk_stride,
+                           const uint32_t *lens /* [n_streams] samples for each stream, 0 = none */,
+                           sr_stream_event *events, uint32_t max_events, uint32_t *n_events);
+int sr_streams_fetch(sr_stream_pool *p, sr_stream_event *events, uint32_t max_events, uint32_t *n_events);
+uint32_t sr_streams_pending(const sr_stream_pool *p);
 int sr_streams_segments(sr_stream_pool *p, uint32_t *seg_off /* [n_streams][3][2] or NULL */, atap_tag *atap /* or NULL */);
+
+/* The same over several GPUs of one box (BASELINE configs[4]): streams [S*g/G, S*(g+1)/G) live on handles[g]; one
+ * persistent host thread per shard (bound to its GPU's NUMA node) runs that shard's push, so the G pushes overlap.
+ * chunk / lens / seg_off / atap are indexed by GLOBAL stream number, events carry global stream numbers. */
+typedef struct sr_stream_group sr_stream_group;
+int sr_stream_group_create(sr_handle *const *handles, uint32_t n_handles, uint32_t n_streams, uint32_t max_samples,
+                           uint32_t n_len, sr_stream_group **out);
+int sr_stream_group_destroy(sr_stream_group *g);
+int sr_stream_group_reset(sr_stream_group *g);
+int sr_stream_group_push(sr_stream_group *g, const uint16_t *chunk, uint32_t chunk_len, uint32_t chunk_stride,
+                         sr_stream_event *events, uint32_t max_events, uint32_t *n_events);
+int sr_stream_group_push_ragged(sr_stream_group *g, const uint16_t *chunk, uint32_t chunk_stride, const uint32_t *lens,
+                                sr_stream_event *events, uint32_t max_events, uint32_t *n_events);
+int sr_stream_group_segments(sr_stream_group *g, uint32_t *seg_off, atap_tag *atap);
 
 /* secondary globals of the reference, batched: fft magnitudes (MFCC.C:27-62) of n frames of
  * `len` (<=1024) s16 samples each -> u32[n][512]; get_dis (DTW.C:45-62) of n row pairs. */

@@ -8,14 +8,22 @@
 #include <deque>
 #include <utility>
 #include "sr_pack_host.h"
+#include "sr_numa.h"
+#include <map>
 
 #ifndef SR_TRANSPORT_AUTO_DEFAULT
 #define SR_TRANSPORT_AUTO_DEFAULT 0      // what mode -1 (automatic) means: 1 = pack when >= 8 CPUs are usable
 #endif
 
+static int device_numa_node(int device) {
+    char id[64] = {0};
+    if (cudaDeviceGetPCIBusId(id, (int)sizeof id, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return numa_node_of_pci(id);
+}
+
 extern "C" {
 
-int sr_abi_version(void) { return 1; }
+int sr_abi_version(void) { return 2; }
 
 int sr_device_count(void) {
     int n = 0;
@@ -47,16 +55,17 @@ int sr_create(int device, sr_handle **out) {
         return fail(nullptr, "sr_create: kernels are built for sm_100a (B200) only", cudaErrorInvalidDevice);
     }
     h->num_sms = prop.multiProcessorCount;
+    h->numa_node = device_numa_node(device);
+    // every failure from here on goes through sr_destroy, which releases whatever has been created so far
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete h; return fail(nullptr, "cudaStreamCreate", e); }
     h->stream = h->own_stream;
-    e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming | cudaEventBlockingSync);   // the packed transport's sender sleeps on it
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) { delete h; return fail(nullptr, "stream/event creation", e); }
-    if (!dev_tables()) { cudaStreamDestroy(h->own_stream); delete h; return fail(nullptr, "table upload", cudaErrorInitializationError); }
+    if (e != cudaSuccess) { sr_destroy(h); return fail(nullptr, "sr_create: stream/event creation", e); }
+    if (!dev_tables()) { sr_destroy(h); return fail(nullptr, "sr_create: table upload", cudaErrorInitializationError); }
     *out = h;
     return 0;
 }
@@ -64,7 +73,8 @@ int sr_create(int device, sr_handle **out) {
 int sr_destroy(sr_handle *h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    sr_comm_destroy(h);
     delete h->pool;
     for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
     DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
@@ -93,18 +103,64 @@ int sr_use_own_stream(sr_handle *h) {
 int sr_sync(sr_handle *h) {
     SR_REQUIRE(h, h != nullptr);
     DeviceGuard g(h->device);
+    if (h->comm) { const int rc = sr_comm_wait(h); if (rc) return rc; }   // collectives issued so far are covered too
     SR_CK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 uint64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
 
+// ---- pinned host memory -------------------------------------------------------------------------------
+// sr_host_alloc_dev places the pages on the NUMA node the GPU hangs off (first touch on that node's CPUs, then
+// cudaHostRegister), so the H2D copy never crosses the socket interconnect; sr_host_alloc is the plain form.
+static std::mutex g_host_mu;
+static std::map<void *, size_t> g_node_allocs;           // node_alloc'ed + registered regions -> length
+
+int sr_device_numa_node(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return -1; }
+    return device_numa_node(device);
+}
+
+int sr_bind_thread_to_device(int device) {
+    const int node = sr_device_numa_node(device);
+    cpu_set_t want;
+    if (node < 0 || numa_node_count() < 2 || !cpus_of_node(node, &want)) return -1;
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+    return node;
+}
+
 void *sr_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
-void sr_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void *sr_host_alloc_dev(int device, size_t bytes) {
+    if (bytes == 0) return nullptr;
+    const int node = sr_device_numa_node(device);
+    if (node < 0 || numa_node_count() < 2) return sr_host_alloc(bytes);     // single node: nothing to place
+    void *p = node_alloc(bytes, node);
+    if (!p) return nullptr;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); node_free(p, bytes); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    g_node_allocs[p] = bytes;
+    return p;
+}
+
+void sr_host_free(void *p) {
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_node_allocs.find(p);
+        if (it != g_node_allocs.end()) { bytes = it->second; g_node_allocs.erase(it); }
+    }
+    if (bytes) { cudaHostUnregister(p); node_free(p, bytes); }
+    else cudaFreeHost(p);
+}
+
+int sr_host_numa_node(const void *p) { return p ? numa_node_of_page(p) : -1; }
 
 // ---- per-kernel timing: event pairs on the launching stream around every kernel -----------------------
 int sr_timing_enable(sr_handle *h, uint32_t max_records) {
@@ -155,6 +211,32 @@ int sr_set_bank(sr_handle *h, const void *bank, uint32_t n_slot, uint32_t slot_s
     if (bytes) SR_CK(h, cudaMemcpyAsync(h->bank_own.p, bank, bytes, cudaMemcpyHostToDevice, h->stream));
     SR_CK(h, cudaStreamSynchronize(h->stream));
     h->bank = h->bank_own.p; h->n_slot = n_slot; h->slot_stride = slot_stride;
+    return 0;
+}
+
+// ---- command labels: commstr[] of main.c:25-31, what spch_recg returns (main.c:295) ---------------------------------
+// default table = the reference's own 18 entries: "0 " .. "9 " and the GBK codes of up/down/front/back/left/right/big/small
+static const uint8_t kRefLabels[18][3] = {
+    {0x30, 0x20, 0}, {0x31, 0x20, 0}, {0x32, 0x20, 0}, {0x33, 0x20, 0}, {0x34, 0x20, 0}, {0x35, 0x20, 0}, {0x36, 0x20, 0},
+    {0x37, 0x20, 0}, {0x38, 0x20, 0}, {0x39, 0x20, 0}, {0xC9, 0xCF, 0}, {0xCF, 0xC2, 0}, {0xC7, 0xB0, 0}, {0xBA, 0xF3, 0},
+    {0xD7, 0xF3, 0}, {0xD3, 0xD2, 0}, {0xB4, 0xF3, 0}, {0xD0, 0xA1, 0}};
+
+int sr_set_labels(sr_handle *h, const void *labels, uint32_t n_labels, uint32_t label_stride) {
+    SR_REQUIRE(h, h && (n_labels == 0 || (labels && label_stride > 0)));
+    h->labels.assign(static_cast<const uint8_t *>(labels), static_cast<const uint8_t *>(labels) + (size_t)n_labels * label_stride);
+    h->n_labels = n_labels; h->label_stride = label_stride;
+    return 0;
+}
+
+const uint8_t *sr_label(const sr_handle *h, uint32_t cmd) {
+    if (h && h->label_stride) return cmd < h->n_labels ? h->labels.data() + (size_t)cmd * h->label_stride : nullptr;
+    return cmd < 18u ? kRefLabels[cmd] : nullptr;                  // no table set: the reference's
+}
+
+int sr_labels_batch(const sr_handle *h, const uint32_t *cmd, const uint8_t *status, uint32_t B, const uint8_t **labels_out) {
+    if (!cmd || !labels_out) return -1;
+    for (uint32_t b = 0; b < B; ++b)                               // NULL = spch_recg's early returns (main.c:261-274)
+        labels_out[b] = (status && status[b] != SR_ST_OK) ? nullptr : sr_label(h, cmd[b]);
     return 0;
 }
 
@@ -385,7 +467,7 @@ int sr_debug_unpack12(sr_handle *h, const uint8_t *packed, uint64_t n, uint16_t 
 // with pinned host memory the call is bound by max(PCIe, compute) instead of their sum.
 int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, const sr_recog_out *o) {
     SR_REQUIRE(h, h && o && (B == 0 || pcm));
-    SR_REQUIRE(h, U <= 65535u && n_len <= U);
+    SR_REQUIRE(h, (B == 0 || U > 0) && U <= 65535u && n_len <= U);
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     const size_t T = h->n_slot;
@@ -567,7 +649,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
 int sr_enrol_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, void *bank_out,
                    uint32_t slot_stride, uint8_t *status) {
     SR_REQUIRE(h, h && (B == 0 || (pcm && bank_out)));
-    SR_REQUIRE(h, U <= 65535u && n_len <= U && slot_stride >= (uint32_t)kFtrBytes && slot_stride % 4 == 0);
+    SR_REQUIRE(h, (B == 0 || U > 0) && U <= 65535u && n_len <= U && slot_stride >= (uint32_t)kFtrBytes && slot_stride % 4 == 0);
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     SR_CK(h, ensure(h->pcm, (size_t)B * U * 2 + 16));

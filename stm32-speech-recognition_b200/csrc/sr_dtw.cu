@@ -78,8 +78,11 @@ __global__ void __launch_bounds__(kK2Warps * 32)
 dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char *__restrict__ bank, u32 T,
            u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best,
            const u8 *__restrict__ status /* may be NULL: per-utterance SR_ST_* gate of sr_recognise */,
-           int Wg, int NU, int G, u32 tile0, int tslots /* template slots allocated in shared memory */) {
+           int Wg, int NU, int G, u32 tile0, int tslots /* template slots allocated in shared memory */,
+           const u32 *__restrict__ B_dev /* optional: batch size produced on the device (streaming) */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (B_dev) B = min(B, *B_dev);
+    if (B == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 t0 = (blockIdx.x + tile0) * kTileT;
     const int Tt = (int)min((u32)kTileT, T - t0);
@@ -95,7 +98,7 @@ dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char 
         u32 frm = hdr >> 16;
         if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;   // main.c:283
         if (frm > 119u && frm != 0xFFFFFFFFu) frm = 0xFFFFFFFEu;                                    // garbage header: no walk
-        const int nrows = (frm >= 0xFFFFFFFEu) ? 0 : (int)min(frm + 1u, 119u);   // +1: the do-while may touch row frm
+        const int nrows = (frm >= 0xFFFFFFFEu) ? 0 : (int)min(max(frm + 1u, 2u), 119u);   // +1: the do-while may touch row frm; rows 0 and 1 are always read (DTW.C:146-160), also when frm_num == 0
         stage_planes(tile + (size_t)tt * kSlotBytes, slot, nrows, lane, 32);
         if (lane == 0) tfrm[tt] = frm;
     }
@@ -121,7 +124,7 @@ dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char 
                 const unsigned char *uf = in_ftr + (size_t)u * kFtrBytes;
                 frm = (*reinterpret_cast<const u32 *>(uf)) >> 16;
                 if (frm > 119u) frm = 0xFFFFFFFEu;
-                else stage_planes(gslots + (size_t)s * kSlotBytes, uf, (int)min(frm + 1u, 119u), gtid, gthreads);
+                else stage_planes(gslots + (size_t)s * kSlotBytes, uf, (int)min(max(frm + 1u, 2u), 119u), gtid, gthreads);
             }
             if (gtid == 0) gfrm[s] = frm;
         }
@@ -320,7 +323,7 @@ __global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
 // one launch for `ntiles` template tiles of width Tt starting at tile `tile0`
 static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags,
                                     u32 *score, u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 tile0,
-                                    u32 ntiles, int Tt) {
+                                    u32 ntiles, int Tt, const u32 *B_dev) {
     // lane packing: groups of Wg warps walk NU utterances x Tt templates; pick the best (Wg, NU, G)
     const size_t budget = 224 * 1024 - (size_t)Tt * kSlotBytes - 128 - 512;
     const int slots_max = (int)(budget / kSlotBytes);
@@ -347,19 +350,19 @@ static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank,
     dim3 grid(ntiles, gy);
     dtw_kernel<<<grid, kK2Warps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
                                                  static_cast<const unsigned char *>(bank), T, slot_stride, flags,
-                                                 score, best, status, bestWg, bestNU, bestG, tile0, Tt);
+                                                 score, best, status, bestWg, bestNU, bestG, tile0, Tt, B_dev);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
-                       u64 *best, const u8 *status, int num_sms, cudaStream_t st) {
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev) {
     if (B == 0 || T == 0) return cudaSuccess;
     const u32 full = T / kTileT, rem = T % kTileT;
     if (full) {
-        cudaError_t e = launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, kTileT);
+        cudaError_t e = launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, kTileT, B_dev);
         if (e != cudaSuccess) return e;
     }
-    if (rem) return launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, (int)rem);
+    if (rem) return launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, (int)rem, B_dev);
     return cudaSuccess;
 }
 cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st) {

@@ -15,11 +15,12 @@ namespace srk {
 cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad, atap_tag *atap,
                        u32 *seg_off, int num_sms, cudaStream_t st);
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
-                        int num_sms, cudaStream_t st, const u32 *row_map = nullptr, u32 rows_total = 0);
+                        int num_sms, cudaStream_t st, const u32 *row_map = nullptr, u32 rows_total = 0,
+                        const u32 *B_dev = nullptr);
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
                                cudaStream_t st);
 cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
-                       u64 *best, const u8 *status, int num_sms, cudaStream_t st);
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev = nullptr);
 cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, int band_r,
                             u32 *score, u64 *best, int num_sms, cudaStream_t st);
 cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st);
@@ -38,6 +39,8 @@ class PackPool;
 using namespace srk;
 
 inline thread_local std::string g_tls_error;
+
+struct sr_comm;                                       // sr_comm.cu: NCCL communicator + its stream
 
 struct DevBuf {
     void *p = nullptr;
@@ -71,6 +74,11 @@ struct sr_handle {
     uint32_t last_packed = 0, last_plain = 0, chunk_seq = 0;
     uint64_t last_h2d = 0;
     DevBuf dpacked;
+    // command labels (commstr, main.c:25-31): n_labels records of label_stride bytes, NUL-terminated
+    std::vector<uint8_t> labels;
+    u32 n_labels = 0, label_stride = 0;
+    sr_comm *comm = nullptr;                           // the exchange step (sr_comm_create), optional
+    int numa_node = -1;                                // node the device hangs off (-1 unknown / single node)
     // grow-only device workspaces
     DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
 };

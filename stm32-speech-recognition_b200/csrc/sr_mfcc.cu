@@ -151,8 +151,10 @@ template <int kConsumerWarps, int kNBuf, bool kSelf>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
                                           unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
-                                          const u32 *__restrict__ row_map, u32 rows_total) {
-    constexpr int kAhead = kNBuf - 2;                      // slot of it+kAhead was last used by utterance it-2
+                                          const u32 *__restrict__ row_map, u32 rows_total, const u32 *__restrict__ B_dev) {
+    constexpr int kAhead = kNBuf - 2;
+    if (B_dev) B = min(B, *B_dev);                         // batch size produced on the device (streaming: segments closed by this push)
+    if (blockIdx.x >= B) return;                      // slot of it+kAhead was last used by utterance it-2
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MfccSmem<kConsumerWarps, kNBuf> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps, kNBuf> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -395,8 +397,9 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                                                          const atap_tag *__restrict__ atap,                       \
                                                          unsigned char *__restrict__ ftr,                         \
                                                          const DevTables *__restrict__ tab,                       \
-                                                         const u32 *__restrict__ row_map, u32 rows_total) {      \
-        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total);                  \
+                                                         const u32 *__restrict__ row_map, u32 rows_total,        \
+                                                         const u32 *__restrict__ B_dev) {                         \
+        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);           \
     }
 SR_MFCC_VARIANT(s16, 16, 4, true, 128)
 SR_MFCC_VARIANT(w15, 15, 3, false, 128)
@@ -457,14 +460,14 @@ fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, cons
 template <int W, int NB, bool SELF, typename K>
 static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride,
                                        const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st,
-                                       const u32 *row_map, u32 rows_total) {
+                                       const u32 *row_map, u32 rows_total, const u32 *B_dev) {
     const size_t smem = sizeof(MfccSmem<W, NB>);
     const int threads = (SELF ? W : W + 1) * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
     kern<<<grid, threads, smem, st>>>(pcm, U, B, seg, seg_stride, atap, static_cast<unsigned char *>(ftr), tab, row_map,
-                                      rows_total);
+                                      rows_total, B_dev);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
@@ -477,7 +480,7 @@ static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, con
 }
 
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
-                        void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total) {
+                        void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total, const u32 *B_dev) {
     if (B == 0) return cudaSuccess;
     const DevTables *tab = dev_tables();
     if (!tab) return cudaErrorInitializationError;
@@ -487,8 +490,8 @@ cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_st
         variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
     }
     if (variant == 15)
-        return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
-    return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
+        return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
+    return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
 }
 
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,

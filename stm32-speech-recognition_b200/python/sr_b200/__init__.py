@@ -76,6 +76,30 @@ def lib():
         L.sr_streams_reset.argtypes = [vp]
         L.sr_streams_push.argtypes = [vp, vp, u32, u32, vp, u32, vp]
         L.sr_streams_segments.argtypes = [vp, vp, vp]
+        L.sr_streams_push_ragged.argtypes = [vp, vp, u32, vp, vp, u32, vp]
+        L.sr_streams_fetch.argtypes = [vp, vp, u32, vp]
+        L.sr_streams_pending.argtypes = [vp]
+        L.sr_streams_pending.restype = u32
+        L.sr_stream_group_create.argtypes = [C.POINTER(vp), u32, u32, u32, u32, C.POINTER(vp)]
+        L.sr_stream_group_destroy.argtypes = [vp]
+        L.sr_stream_group_reset.argtypes = [vp]
+        L.sr_stream_group_push.argtypes = [vp, vp, u32, u32, vp, u32, vp]
+        L.sr_stream_group_push_ragged.argtypes = [vp, vp, u32, vp, vp, u32, vp]
+        L.sr_stream_group_segments.argtypes = [vp, vp, vp]
+        L.sr_host_alloc_dev.argtypes = [i32, C.c_size_t]
+        L.sr_host_alloc_dev.restype = vp
+        L.sr_bind_thread_to_device.argtypes = [i32]
+        L.sr_device_numa_node.argtypes = [i32]
+        L.sr_host_numa_node.argtypes = [vp]
+        L.sr_comm_unique_id.argtypes = [vp]
+        L.sr_comm_create.argtypes = [vp, i32, i32, vp]
+        L.sr_comm_destroy.argtypes = [vp]
+        L.sr_comm_wait.argtypes = [vp]
+        L.sr_allgather_dev.argtypes = [vp, vp, vp, C.c_size_t]
+        L.sr_recognise_batch_dev_allgather.argtypes = [vp, vp, u32, u32, u32, C.POINTER(RecogOut), vp, vp]
+        L.sr_set_labels.argtypes = [vp, vp, u32, u32]
+        L.sr_label.argtypes = [vp, u32]
+        L.sr_label.restype = vp
         L.sr_set_bank.argtypes = [vp, vp, u32, u32]
         L.sr_set_bank_dev.argtypes = [vp, vp, u32, u32]
         for name in ("sr_noise_atap_batch", "sr_noise_atap_batch_dev"):
@@ -301,10 +325,45 @@ class Handle:
     def dtw_dev(self, ftr_ptr, B, flags, band_r, score_ptr, bi_ptr, bd_ptr):
         self._ck(lib().sr_dtw_batch_dev(self._h, _p(ftr_ptr), B, flags, band_r, _p(score_ptr), _p(bi_ptr), _p(bd_ptr)))
 
+    # -- the exchange step (NCCL behind the C-ABI)
+    def comm_create(self, rank, world, id_bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id_bytes))
+        self._ck(lib().sr_comm_create(self._h, rank, world, buf))
+
+    def comm_wait(self):
+        self._ck(lib().sr_comm_wait(self._h))
+
+    def allgather_dev(self, send_ptr, recv_ptr, nbytes):
+        self._ck(lib().sr_allgather_dev(self._h, _p(send_ptr), _p(recv_ptr), nbytes))
+
+    def recognise_dev_allgather(self, pcm_ptr, U, B, n_len, gathered_score=None, gathered_best=None, **ptrs):
+        ro = RecogOut(*[_p(ptrs.get(k)) for k in
+                        ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
+        self._ck(lib().sr_recognise_batch_dev_allgather(self._h, _p(pcm_ptr), U, B, n_len, C.byref(ro),
+                                                         _p(gathered_score), _p(gathered_best)))
+
+    def label(self, cmd):
+        """bytes of the command label (commstr, main.c:25-31) or None"""
+        p = lib().sr_label(self._h, int(cmd))
+        return C.string_at(p) if p else None
+
+    def set_labels(self, labels, stride):
+        raw = b"".join(bytes(l)[:stride - 1].ljust(stride, b"\0") for l in labels)
+        self._ck(lib().sr_set_labels(self._h, raw, len(labels), stride))
+
     def recognise_dev(self, pcm_ptr, U, B, n_len, **ptrs):
         ro = RecogOut(*[_p(ptrs.get(k)) for k in
                         ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
         self._ck(lib().sr_recognise_batch_dev(self._h, _p(pcm_ptr), U, B, n_len, C.byref(ro)))
+
+
+def comm_unique_id():
+    """128 bytes identifying a new communicator (call on one rank, hand to the others)"""
+    buf = (C.c_uint8 * 128)()
+    rc = lib().sr_comm_unique_id(buf)
+    if rc != 0:
+        raise SrError("sr_comm_unique_id failed (%d): %s" % (rc, lib().sr_last_error(None).decode()))
+    return bytes(buf)
 
 
 def recognise_multi(handles, pcm, n_len=2400, want=("best_idx", "best_dis", "cmd", "status", "score", "seg_off")):
@@ -333,37 +392,91 @@ def recognise_multi(handles, pcm, n_len=2400, want=("best_idx", "best_dis", "cmd
 
 
 class StreamPool:
-    """sr_stream_pool wrapper: lock-step chunked capture of S streams (include/speech_recog.h, streaming section)"""
+    """sr_stream_pool / sr_stream_group wrapper: chunked capture of S streams, in lock step or ragged
+    (include/speech_recog.h, streaming section). `handle` may be a list of handles: the streams are then sharded over
+    them (one GPU each)."""
 
     def __init__(self, handle, n_streams, max_samples, n_len=2400):
-        self.h, self.S, self.L = handle, n_streams, max_samples
+        self.S, self.L = n_streams, max_samples
         self._p = C.c_void_p()
-        handle._ck(lib().sr_streams_create(handle._h, n_streams, max_samples, n_len, C.byref(self._p)))
+        self.group = isinstance(handle, (list, tuple))
+        self.h = handle[0] if self.group else handle
+        if self.group:
+            arr = (C.c_void_p * len(handle))(*[h._h for h in handle])
+            rc = lib().sr_stream_group_create(arr, len(handle), n_streams, max_samples, n_len, C.byref(self._p))
+            if rc != 0:
+                raise SrError("sr_stream_group_create failed (%d): %s" % (rc, lib().sr_last_error(None).decode()))
+        else:
+            handle._ck(lib().sr_streams_create(handle._h, n_streams, max_samples, n_len, C.byref(self._p)))
         self._ev = (StreamEvent * (3 * n_streams))()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SrError("streaming call failed (%d): %s" % (rc, (lib().sr_last_error(None) or b"").decode()))
 
     def close(self):
         if self._p:
-            lib().sr_streams_destroy(self._p)
+            (lib().sr_stream_group_destroy if self.group else lib().sr_streams_destroy)(self._p)
             self._p = C.c_void_p()
 
     def reset(self):
-        self.h._ck(lib().sr_streams_reset(self._p))
+        self._ck((lib().sr_stream_group_reset if self.group else lib().sr_streams_reset)(self._p))
 
-    def push(self, chunk, chunk_len=None, stride=None):
+    def _events(self, n):
+        return [{k: getattr(self._ev[i], k) for k, _ in StreamEvent._fields_} for i in range(n)]
+
+    def push(self, chunk, chunk_len=None, stride=None, max_events=None):
         """chunk: numpy [S, chunk_len] u16 (or a raw host pointer with chunk_len/stride). Returns list of event dicts."""
         if isinstance(chunk, np.ndarray):
             chunk_len, stride, ptr = chunk.shape[1], chunk.strides[0] // 2, chunk.ctypes.data_as(C.c_void_p)
         else:
             ptr = C.c_void_p(int(chunk))
         n = C.c_uint32(0)
-        self.h._ck(lib().sr_streams_push(self._p, ptr, chunk_len, stride, self._ev, 3 * self.S, C.byref(n)))
-        return [{k: getattr(self._ev[i], k) for k, _ in StreamEvent._fields_} for i in range(n.value)]
+        f = lib().sr_stream_group_push if self.group else lib().sr_streams_push
+        self._ck(f(self._p, ptr, chunk_len, stride, self._ev, 3 * self.S if max_events is None else max_events, C.byref(n)))
+        return self._events(n.value)
+
+    def push_ragged(self, chunk, lens, stride=None, max_events=None):
+        """chunk: numpy [S, >= max(lens)] u16 (or raw pointer + stride); lens: [S] samples for each stream"""
+        lens = np.ascontiguousarray(lens, np.uint32)
+        if isinstance(chunk, np.ndarray):
+            stride, ptr = chunk.strides[0] // 2, chunk.ctypes.data_as(C.c_void_p)
+        else:
+            ptr = C.c_void_p(int(chunk))
+        n = C.c_uint32(0)
+        f = lib().sr_stream_group_push_ragged if self.group else lib().sr_streams_push_ragged
+        self._ck(f(self._p, ptr, stride, _p(lens), self._ev, 3 * self.S if max_events is None else max_events, C.byref(n)))
+        return self._events(n.value)
+
+    def fetch(self, max_events=None):
+        assert not self.group
+        n = C.c_uint32(0)
+        self._ck(lib().sr_streams_fetch(self._p, self._ev, 3 * self.S if max_events is None else max_events, C.byref(n)))
+        return self._events(n.value)
+
+    def pending(self):
+        return int(lib().sr_streams_pending(self._p))
 
     def segments(self):
         seg = np.zeros((self.S, 3, 2), np.uint32)
         atap = np.zeros(self.S, ATAP_DTYPE)
-        self.h._ck(lib().sr_streams_segments(self._p, _p(seg), _p(atap)))
+        f = lib().sr_stream_group_segments if self.group else lib().sr_streams_segments
+        self._ck(f(self._p, _p(seg), _p(atap)))
         return seg, atap
+
+
+def host_alloc_dev(device, nbytes):
+    """pinned host memory on `device`'s NUMA node as a numpy uint8 array (keeps the allocation alive through .base)"""
+    p = lib().sr_host_alloc_dev(int(device), nbytes)
+    if not p:
+        raise SrError("sr_host_alloc_dev(%d, %d) failed" % (device, nbytes))
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    arr = np.frombuffer(buf, np.uint8)
+    return arr, p
+
+
+def host_free(p):
+    lib().sr_host_free(C.c_void_p(p))
 
 
 # ---- synthetic workload (include/sr_synth.h) -------------------------------------------------------

@@ -287,6 +287,20 @@ def test_dtw_limit_batch_and_drop_in_symbol(handle, ora):
     I, M = int(f["frm_num"][0]), int(f["frm_num"][1])
     for x, y in ((1, 1), (5, 20), (20, 5), (I, M), (2, 9)):
         assert L.dtw_limit(x, y) == po.lib.sro_dtw_limit(x, y, I, M)
+    # ... and against the reference's OWN dtw_limit, which reads the file statics its dtw() left behind (DTW.C:65-68,
+    # 130-131, 141-142): call dtw() in libref, then compare every lattice point of that shape with the drop-in symbol
+    if ob.have_ref():
+        r = ob.ref()
+        for seed, lo, hi in ((0xABC, 30, 40), (0x51, 50, 100), (0x52, 8, 15), (0x53, 100, 119)):
+            f = sr_b200.synth_ftr_host(2, seed, lo, hi).view(sr_b200.FTR_DTYPE).reshape(-1)
+            if seed == 0x51:
+                f["frm_num"][0], f["frm_num"][1] = 50, 100        # the 2:1 edge of the guard (DTW.C:133)
+            pa, pb = f[0:1].ctypes.data_as(C.c_void_p), f[1:2].ctypes.data_as(C.c_void_p)
+            assert L.dtw(pa, pb) == r.lib.dtw(pa, pb)
+            I, M = int(f["frm_num"][0]), int(f["frm_num"][1])
+            mine = [L.dtw_limit(x, y) for x in range(0, I + 3) for y in range(0, M + 3)]
+            theirs = [r.lib.dtw_limit(C.c_uint16(x), C.c_uint16(y)) for x in range(0, I + 3) for y in range(0, M + 3)]
+            assert mine == theirs and 0 < sum(theirs) < len(theirs), (seed, I, M)
 
 
 def test_dtw_fuzz_many_pairs(handle, ora):
@@ -321,6 +335,46 @@ def test_dtw_all_lengths_bit_exact(handle, ora):
     want_s, _ = ora.dtw_batch(ftr, bank, T, 4096, check_sign=1)
     score_s, _, _ = handle.dtw(ftr, flags=sr_b200.DTW_CHECK_SIGN)
     assert np.array_equal(score_s, want_s) and (score_s[:, 5] == ob.NULL).all()
+
+
+def test_dtw_200_templates_mixed_save_sign(handle, ora):
+    """configs[2] bank width: T = 200 = 6 full template tiles + a remainder launch, a third of the slots erased / unsigned
+    (main.c:283), against the reference's own dtw; argmin = strict '<' first-wins scan over the 200 slots (main.c:285-289)"""
+    B, T = 96, 200
+    fin = sr_b200.synth_ftr_host(B, 0xD7A00000, 50, 100).view(sr_b200.FTR_DTYPE).reshape(-1)
+    bank = sr_b200.synth_ftr_host(T, 0xD7A10000, 50, 100, stride=4096)
+    rng = np.random.default_rng(200)
+    bad = rng.random(T) < 0.33
+    bank[bad, 0:2] = 0xFF                                  # erased flash: save_sign != 12345
+    bank[~bad, 0], bank[~bad, 1] = 12345 & 0xFF, 12345 >> 8
+    bank[7] = bank[3]                                      # an exact duplicate: first wins
+    handle.set_bank(bank, T, 4096)
+    score, bi, bd = handle.dtw(fin, flags=sr_b200.DTW_CHECK_SIGN)
+    want, _ = ora.dtw_batch(fin, bank, T, 4096, check_sign=1)
+    assert np.array_equal(score, want)
+    assert (score[:, bad] == ob.NULL).all() and (score[:, ~bad] != ob.NULL).any()
+    key = (want.astype(np.uint64) << np.uint64(32)) | np.arange(T, dtype=np.uint64)[None, :]
+    k = key.min(axis=1)
+    assert np.array_equal(bi, (k & np.uint64(0xFFFFFFFF)).astype(np.uint32)) and np.array_equal(bd, (k >> np.uint64(32)).astype(np.uint32))
+    # same bank without the save_sign check (dtw() itself never looks at it)
+    score2, _, _ = handle.dtw(fin)
+    want2, _ = ora.dtw_batch(fin, bank, T, 4096, check_sign=0)
+    assert np.array_equal(score2, want2)
+
+
+def test_dtw_empty_feature_sets_are_deterministic(handle, ora):
+    """frm_num == 0 on both sides passes the 2:1 guard (DTW.C:133) and the do-while still reads rows 0 and 1 of both
+    structs (DTW.C:146-160): the result is defined by the struct bytes, not by whatever was staged before"""
+    f = sr_b200.synth_ftr_host(6, 0xE0, 20, 30).view(sr_b200.FTR_DTYPE).reshape(-1).copy()
+    f["frm_num"][:3] = 0                                   # rows stay: the reference reads them
+    bank = np.zeros((4, 4096), np.uint8)
+    bank[:, :2860] = f[[0, 1, 3, 4]].view(np.uint8).reshape(4, 2860)
+    handle.set_bank(bank, 4, 4096)
+    for _ in range(2):                                     # twice: the second run sees different leftovers in shared memory
+        score, _, _ = handle.dtw(f)
+        want, _ = ora.dtw_batch(f, bank, 4, 4096)
+        assert np.array_equal(score, want)
+        handle.dtw(sr_b200.synth_ftr_host(64, 0xE1, 90, 119).view(sr_b200.FTR_DTYPE).reshape(-1))
 
 
 def test_dtw_extreme_values_wrap(handle, ora):
@@ -567,6 +621,118 @@ def test_streaming_equals_batch(handle, ora, chunk):
         key = (sc[0].astype(np.uint64) << np.uint64(32)) | np.arange(T, dtype=np.uint64)
         assert e["best_dis"] == int(key.min() >> np.uint64(32)) and e["best_idx"] == int(key.min() & np.uint64(0xFFFFFFFF))
         assert e["cmd"] == e["best_idx"] // 4
+
+
+def _check_stream_events(handle, ora, pcm, bank, T, events, seg, atap):
+    S = pcm.shape[0]
+    batch_atap = handle.noise_atap(pcm, 2400)
+    assert atap.tobytes() == batch_atap.tobytes()
+    batch_seg = handle.vad(pcm, batch_atap)
+    assert np.array_equal(seg, batch_seg)
+    closed = [(s, k) for s in range(S) for k in range(3) if batch_seg[s, k, 1] != ob.NULL]
+    assert sorted((e["stream"], e["segment"]) for e in events) == closed and len(closed) >= 2 * S
+    want = handle.recognise(pcm, 2400, want=("best_idx", "best_dis", "cmd", "status"))     # segment 0 == the batch call
+    for e in events:
+        s, k = e["stream"], e["segment"]
+        assert (e["start"], e["end"]) == tuple(batch_seg[s, k])
+        if k == 0:
+            assert (e["best_idx"], e["best_dis"], e["cmd"], e["status"]) == tuple(int(want[q][s]) for q in ("best_idx", "best_dis", "cmd", "status"))
+    for e in events[:: max(1, len(events) // 12)]:           # a sample against the oracle, segment by segment
+        s, k = e["stream"], e["segment"]
+        f = ora.mfcc_batch(pcm[s:s + 1], batch_seg[s, k].reshape(1, 2), batch_atap[s:s + 1])
+        assert e["frm_num"] == int(f["frm_num"][0]) and e["status"] == 0
+        sc, _ = ora.dtw_batch(f, bank, T, 4096, check_sign=1)
+        key = (sc[0].astype(np.uint64) << np.uint64(32)) | np.arange(T, dtype=np.uint64)
+        assert e["best_dis"] == int(key.min() >> np.uint64(32)) and e["best_idx"] == int(key.min() & np.uint64(0xFFFFFFFF))
+
+
+def test_streaming_ragged_arrival_equals_batch(handle, ora):
+    """every stream advances at its own pace (random chunk lengths incl. 0 and odd ones, some streams far ahead of
+    others, a stream that starts late): events and final segments still equal the batch results"""
+    S, L, T = 40, 40000, 8
+    pcm = sr_b200.synth_pcm_host(S, L, 0x5EED6000, 3)
+    bank = GOLD["synth/bank"]
+    handle.set_bank(bank, T, 4096)
+    pool = sr_b200.StreamPool(handle, S, L, 2400)
+    rng = np.random.default_rng(77)
+    pos = np.zeros(S, np.int64)
+    events, pushes = [], 0
+    while (pos < L).any():
+        lens = rng.choice([0, 1, 79, 80, 81, 160, 333, 800, 1601, 4000], S).astype(np.int64)
+        lens[5] = 0 if pushes < 30 else lens[5]            # stream 5 starts late
+        lens = np.minimum(lens, L - pos)
+        w = int(lens.max())
+        if w == 0:
+            continue
+        chunk = np.zeros((S, w), np.uint16)
+        for s in range(S):
+            chunk[s, :lens[s]] = pcm[s, pos[s]:pos[s] + lens[s]]
+        evs = pool.push_ragged(chunk, lens)
+        for e in evs:                                       # an event appears with the push that delivers sample end+879
+            s = e["stream"]
+            assert pos[s] <= e["end"] + 879 < pos[s] + lens[s], (e, pos[s], lens[s])
+        events += evs
+        pos += lens
+        pushes += 1
+    seg, atap = pool.segments()
+    pool.close()
+    _check_stream_events(handle, ora, pcm, bank, T, events, seg, atap)
+
+
+def test_streaming_small_event_buffer_keeps_events(handle, ora):
+    """max_events smaller than what a push closes: nothing is lost, the rest comes with later pushes / sr_streams_fetch"""
+    S, L, T = 32, 16000, 8
+    pcm = sr_b200.synth_pcm_host(S, L, 0x5EED7000, 1)
+    handle.set_bank(GOLD["synth/bank"], T, 4096)
+    pool = sr_b200.StreamPool(handle, S, L, 2400)
+    full = []
+    for n0 in range(0, L, 4000):
+        full += pool.push(np.ascontiguousarray(pcm[:, n0:n0 + 4000]))
+    pool.reset()
+    got = []
+    for n0 in range(0, L, 4000):
+        evs = pool.push(np.ascontiguousarray(pcm[:, n0:n0 + 4000]), max_events=3)
+        assert len(evs) <= 3
+        got += evs
+    assert pool.pending() == len(full) - len(got) > 0
+    while pool.pending():
+        got += pool.fetch(max_events=5)
+    pool.close()
+    assert got == full and len(full) >= S - 2
+
+
+def test_stream_group_shards_streams_over_handles(handle, ora):
+    """sr_stream_group: streams sharded over several handles (all visible GPUs, or two handles on one GPU), lock-step and
+    ragged pushes; events carry global stream numbers and equal the batch results"""
+    import torch
+    ng = max(1, torch.cuda.device_count())
+    devs = list(range(ng)) if ng > 1 else [0, 0]
+    S, L, T = 37, 40000, 8
+    pcm = sr_b200.synth_pcm_host(S, L, 0x5EED8000, 3)
+    bank = GOLD["synth/bank"]
+    hs = [sr_b200.Handle(d) for d in devs]
+    for h in hs:
+        h.set_bank(bank, T, 4096)
+    handle.set_bank(bank, T, 4096)
+    pool = sr_b200.StreamPool(hs, S, L, 2400)
+    events = []
+    for n0 in range(0, 20000, 800):
+        events += pool.push(np.ascontiguousarray(pcm[:, n0:n0 + 800]))
+    rng = np.random.default_rng(5)
+    pos = np.full(S, 20000, np.int64)
+    while (pos < L).any():
+        lens = np.minimum(rng.integers(0, 1500, S), L - pos)
+        w = max(int(lens.max()), 1)
+        chunk = np.zeros((S, w), np.uint16)
+        for s in range(S):
+            chunk[s, :lens[s]] = pcm[s, pos[s]:pos[s] + lens[s]]
+        events += pool.push_ragged(chunk, lens)
+        pos += lens
+    seg, atap = pool.segments()
+    pool.close()
+    _check_stream_events(handle, ora, pcm, bank, T, events, seg, atap)
+    for h in hs:
+        h.close()
 
 
 def test_recognise_multi_handle_sharding(ora):
