@@ -12,7 +12,7 @@
 #include <map>
 
 #ifndef SR_TRANSPORT_AUTO_DEFAULT
-#define SR_TRANSPORT_AUTO_DEFAULT 0      // what mode -1 (automatic) means: 1 = pack when >= 8 CPUs are usable
+#define SR_TRANSPORT_AUTO_DEFAULT 1      // what mode -1 (automatic) means: 1 = pack when this rank's share of the CPUs is >= 6
 #endif
 
 static int device_numa_node(int device) {
@@ -418,13 +418,20 @@ int sr_dtw_batch(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, 
     return 0;
 }
 
+// CPUs this rank may count on: the process' usable CPUs (affinity capped by the cgroup quota) divided by the ranks that
+// share them (torchrun exports LOCAL_WORLD_SIZE)
+static int rank_cpu_share() {
+    static const int local_world = [] { const char *e = getenv("LOCAL_WORLD_SIZE"); const int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();
+    return usable_cpus() / local_world;
+}
+
 static bool transport_enabled(const sr_handle *h) {
     int mode = h->transport_mode;
     if (mode < 0) {
         static const int env_mode = [] { const char *e = getenv("SR_PACK12"); return e && *e ? atoi(e) : -1; }();
         mode = env_mode;
     }
-    if (mode < 0) mode = SR_TRANSPORT_AUTO_DEFAULT && usable_cpus() >= 8 ? 1 : 0;
+    if (mode < 0) mode = SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6 ? 1 : 0;
     return mode > 0;
 }
 
@@ -533,12 +540,11 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     bool packed_transport = nchunks >= 4 && transport_enabled(h);
     if (packed_transport) {                              // workers, pinned staging slots, device staging
         const size_t pk = ((((size_t)chunk * U + 1) / 2 * 3 + 64 + 255) / 256) * 256;
+        ScopedNodeAffinity node_scope(h->numa_node);      // workers inherit it; staging pages are allocated from this node
         if (!h->pool) {
-            // leave room under a cgroup CPU quota for the sender, the CUDA runtime's threads and the caller's own work
+            // packers = this rank's CPU share minus room for the sender, the CUDA runtime's threads and the caller's own work
             static const int env_nt = [] { const char *e = getenv("SR_PACK_THREADS"); return e && *e ? atoi(e) : 0; }();
-            // under torchrun the ranks of one node share the CPU quota
-            static const int local_world = [] { const char *e = getenv("LOCAL_WORLD_SIZE"); const int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();
-            int nt = env_nt > 0 ? env_nt : usable_cpus() / local_world - 4;
+            int nt = env_nt > 0 ? env_nt : rank_cpu_share() - 3;
             nt = nt > 16 ? 16 : nt;
             if (nt >= 2) h->pool = new (std::nothrow) PackPool(nt);
         }
@@ -572,6 +578,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         unsigned free_mask = (1u << sr_handle::kStage) - 1u;
         bool abort = false;
         std::thread packer([&] {
+            ScopedNodeAffinity bind(h->numa_node);        // slice 0 of every chunk is packed by this thread
             for (;;) {
                 int slot;
                 uint32_t c;

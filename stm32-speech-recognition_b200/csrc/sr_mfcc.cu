@@ -37,18 +37,17 @@
 namespace srk {
 
 constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
-constexpr int kFftWords = 1024 + 64;         // +4 words per 64
+constexpr int kFftWords = kFftWordsTotal;    // FFT data: 1024 + 4 words per 64; filter-stage scratch behind it (sr_common.cuh)
 
 template <int kConsumerWarps, int kNBuf>
 struct __align__(16) MfccSmem {
     unsigned char pcm[kNBuf][kPcmBufBytes];
     int2 tw[340 * 3];
     u32 log_thr[2220];
-    u16 tri_even[512];
-    u16 tri_odd[512];
+    u32 tri_even[512];                       // filter weights as 32-bit words: no unpacking in the frame loop
+    u32 tri_odd[512];
     u32 fftbuf[kConsumerWarps][kFftWords];
     s32 wq[kConsumerWarps][160];
-    u32 seq[kConsumerWarps][2][64];
     u32 lg[kConsumerWarps][32];
     u64 full[kNBuf];
     u64 empty[kNBuf];
@@ -163,6 +162,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     for (int i = threadIdx.x; i < 340 * 3; i += blockDim.x) sm.tw[i] = tab->tw[i];
     for (int i = threadIdx.x; i < 2220; i += blockDim.x) sm.log_thr[i] = tab->log_thr[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) { sm.tri_even[i] = tab->tri_even[i]; sm.tri_odd[i] = tab->tri_odd[i]; }
+    for (int i = threadIdx.x; i < kConsumerWarps; i += blockDim.x) sm.fftbuf[i][kFltZero] = 0u;   // S(512)'s in-lane part
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNBuf; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
         mbar_fence_init();
@@ -198,9 +198,13 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     const int2 k1_2 = sm.tw[q1 * 3 + 1], k1_1 = sm.tw[q1 * 3 + 2];
     const u32 hm0 = tab->hamm[lane], hm1 = tab->hamm[lane + 32], hm2 = tab->hamm[lane + 64],
               hm3 = tab->hamm[lane + 96], hm4 = tab->hamm[lane + 128];
-    const int sp_e = tab->split_even[lane], sp_o = tab->split_odd[lane];
-    int flo = 0, fhi = -1, fpar = 0;
-    if (lane < 24) { flo = tab->seq_lo[lane]; fhi = tab->seq_hi[lane]; fpar = lane & 1; }
+    // filter role: lanes 0..23 -> filter h = lane: S(hi) - S(lo) of its parity's prefix sums (see DevTables)
+    const int fsw = (lane >> 1) & 3;                       // bank swizzle of the running-total rows (flt_word)
+    int fe_lo = kFltZero, fe_hi = kFltZero, fx_lo = kFltX, fx_hi = kFltX;
+    if (lane < 24) {
+        fe_lo = tab->flt_e_lo[lane]; fe_hi = tab->flt_e_hi[lane];
+        fx_lo = kFltX + (lane & 1) * 33 + tab->flt_x_lo[lane]; fx_hi = kFltX + (lane & 1) * 33 + tab->flt_x_hi[lane];
+    }
     // DCT role: lanes 0..23 -> coefficient c = lane>>1, half = lane&1 (12 filters each)
     s32 dctk[12];
 #pragma unroll
@@ -329,39 +333,45 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
             __syncwarp();
 
             // ---- triangular filters, MFCC.C:136-162: lane owns bins [16*lane, 16*lane+16) ------
+            // acc[h] = sum over the filter's bins of (E[k]*tri[k])/100, u32 wrap. Per parity the per-bin terms become
+            // prefix sums: a lane keeps the running totals of its 16 bins (written to the warp's scratch), the lane
+            // totals are scanned over the warp, and a filter is a difference of two prefix values -- exact mod 2^32.
             {
                 u32 E[16];
                 const uint4 *e4 = reinterpret_cast<const uint4 *>(fb + 16 * lane + 4 * (lane >> 2));   // padF(16*lane)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const uint4 v = e4[j]; E[4 * j] = v.x; E[4 * j + 1] = v.y; E[4 * j + 2] = v.z; E[4 * j + 3] = v.w; }
-                const uint4 *te4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
-                const uint4 *to4 = reinterpret_cast<const uint4 *>(sm.tri_odd + 16 * lane);
-                u32 te[8], to[8];
-                { const uint4 a = te4[0], c = te4[1]; te[0] = a.x; te[1] = a.y; te[2] = a.z; te[3] = a.w; te[4] = c.x; te[5] = c.y; te[6] = c.z; te[7] = c.w; }
-                { const uint4 a = to4[0], c = to4[1]; to[0] = a.x; to[1] = a.y; to[2] = a.z; to[3] = a.w; to[4] = c.x; to[5] = c.y; to[6] = c.z; to[7] = c.w; }
-                // running totals; the part below the lane's filter boundary is the total captured at i + 1 == split.
-                // (the empty asm keeps the 32 frame-invariant compares from being hoisted out of the frame loop, where
-                // ptxas would pack them into a bit mask that costs ~100 instructions per frame to rebuild and unpack)
-                int spe = sp_e, spo = sp_o;
-                asm volatile("" : "+r"(spe), "+r"(spo));
-                u32 s0e = 0, tote = 0, s0o = 0, toto = 0;
+                __syncwarp();                                               // every lane holds its energies: fb is scratch now
+                const uint4 *we4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
+                const uint4 *wo4 = reinterpret_cast<const uint4 *>(sm.tri_odd + 16 * lane);
+                uint4 *re4 = reinterpret_cast<uint4 *>(fb + 16 * lane);                    // this lane's row, group g at slot g ^ fsw
+                uint4 *ro4 = reinterpret_cast<uint4 *>(fb + kFltRowWords + 16 * lane);
+                u32 te = 0, to = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const u32 we = (i & 1) ? (te[i >> 1] >> 16) : (te[i >> 1] & 0xFFFFu);
-                    const u32 wo = (i & 1) ? (to[i >> 1] >> 16) : (to[i >> 1] & 0xFFFFu);
-                    const u32 ve = (E[i] * we) / 100u, vo = (E[i] * wo) / 100u;
-                    tote += ve; toto += vo;
-                    if (i + 1 == spe) s0e = tote;
-                    if (i + 1 == spo) s0o = toto;
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 we = we4[j], wo = wo4[j];
+                    uint4 pe, po;                                           // running totals BEFORE bin 4j+c
+                    pe.x = te; te += (E[4 * j] * we.x) / 100u;      po.x = to; to += (E[4 * j] * wo.x) / 100u;
+                    pe.y = te; te += (E[4 * j + 1] * we.y) / 100u;  po.y = to; to += (E[4 * j + 1] * wo.y) / 100u;
+                    pe.z = te; te += (E[4 * j + 2] * we.z) / 100u;  po.z = to; to += (E[4 * j + 2] * wo.z) / 100u;
+                    pe.w = te; te += (E[4 * j + 3] * we.w) / 100u;  po.w = to; to += (E[4 * j + 3] * wo.w) / 100u;
+                    re4[j ^ fsw] = pe; ro4[j ^ fsw] = po;
                 }
-                *reinterpret_cast<uint2 *>(&sm.seq[warp][0][2 * lane]) = make_uint2(s0e, tote - s0e);
-                *reinterpret_cast<uint2 *>(&sm.seq[warp][1][2 * lane]) = make_uint2(s0o, toto - s0o);
+                // X[l] = sum of the lane totals below lane l; X[32] = grand total (the upper end of filter 23 is bin 512)
+                u32 ie = te, io = to;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 ue = __shfl_up_sync(0xFFFFFFFFu, ie, o), uo = __shfl_up_sync(0xFFFFFFFFu, io, o);
+                    if (lane >= o) { ie += ue; io += uo; }
+                }
+                fb[kFltX + lane] = ie - te;
+                fb[kFltX + 33 + lane] = io - to;
+                if (lane == 31) { fb[kFltX + 32] = ie; fb[kFltX + 33 + 32] = io; }
             }
             __syncwarp();
             // ---- filter totals + log, MFCC.C:165-170 -------------------------------------------
             {
-                u32 acc = 0;
-                for (int e = flo; e <= fhi; ++e) acc += sm.seq[warp][fpar][e];
+                const u32 acc = (fb[fx_hi] + fb[fe_hi]) - (fb[fx_lo] + fb[fe_lo]);
                 sm.lg[warp][lane] = (lane < 24) ? log100(acc, sm.log_thr) : 0u;
             }
             __syncwarp();

@@ -7,6 +7,7 @@
 // (unpack12_kernel). Any chunk holding a sample >= 4096 is sent as it is, so the call stays exact for every u16
 // input. Plain C++ (built with g++, not nvcc) so that the SIMD variants can use target attributes.
 #include <immintrin.h>
+#include <x86intrin.h>
 #include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -157,18 +158,23 @@ int usable_cpus() {
 }
 
 // ---- fork-join pool: run() packs one range with all workers ---------------------------------------------------------
+// The pool is used in bursts (one fork-join per 32 MB chunk, back to back for the duration of one sr_recognise_batch
+// call), so workers SPIN briefly for the next job before they go to sleep on the condition variable: a futex wake-up
+// per worker per chunk (~50 us each way) would cost as much as packing the chunk. The caller of run() packs a slice
+// itself instead of idling.
 struct PackPool::Impl {
     std::vector<std::thread> th;
     std::mutex m;
-    std::condition_variable cv_go, cv_done;
-    uint64_t gen = 0;
-    int remaining = 0;
-    bool stop = false;
+    std::condition_variable cv_go;
+    std::atomic<uint64_t> gen{0};
+    std::atomic<int> remaining{0};
+    std::atomic<int> sleepers{0};
+    std::atomic<bool> stop{false};
     const uint16_t *src = nullptr;
     uint8_t *dst = nullptr;
     size_t n = 0;
     std::atomic<uint32_t> orbits{0};
-    int nthreads = 0;
+    int nthreads = 0;                                   // slices per job = workers + the caller
 
     void slice(int t) {
         // slices are multiples of 128 samples (192 packed bytes, three cache lines): no two workers touch the same line
@@ -182,29 +188,36 @@ struct PackPool::Impl {
     void worker(int t) {
         uint64_t seen = 0;
         for (;;) {
-            {
+            bool got = false;
+            const uint64_t t0 = __rdtsc();
+            while (!got) {                                               // poll ~150 us (at ~2-3 GHz TSC) between chunks
+                if (stop.load(std::memory_order_acquire)) return;
+                if (gen.load(std::memory_order_acquire) != seen) got = true;
+                else if (__rdtsc() - t0 > 400000ull) break;
+                else _mm_pause();
+            }
+            if (!got) {
                 std::unique_lock<std::mutex> lk(m);
-                cv_go.wait(lk, [&] { return stop || gen != seen; });
-                if (stop) return;
-                seen = gen;
+                sleepers.fetch_add(1, std::memory_order_relaxed);
+                cv_go.wait(lk, [&] { return stop.load(std::memory_order_acquire) || gen.load(std::memory_order_acquire) != seen; });
+                sleepers.fetch_sub(1, std::memory_order_relaxed);
+                if (stop.load(std::memory_order_acquire)) return;
             }
+            seen = gen.load(std::memory_order_acquire);
             slice(t);
-            {
-                std::lock_guard<std::mutex> lk(m);
-                if (--remaining == 0) cv_done.notify_all();
-            }
+            remaining.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
 };
 
 PackPool::PackPool(int nthreads) : p(new Impl) {
     p->nthreads = nthreads < 1 ? 1 : nthreads;
-    for (int t = 0; t < p->nthreads; ++t) p->th.emplace_back([this, t] { p->worker(t); });
+    for (int t = 1; t < p->nthreads; ++t) p->th.emplace_back([this, t] { p->worker(t); });   // slice 0 is the caller's
 }
 PackPool::~PackPool() {
     {
         std::lock_guard<std::mutex> lk(p->m);
-        p->stop = true;
+        p->stop.store(true, std::memory_order_release);
     }
     p->cv_go.notify_all();
     for (auto &t : p->th) t.join();
@@ -212,13 +225,16 @@ PackPool::~PackPool() {
 }
 int PackPool::threads() const { return p->nthreads; }
 uint32_t PackPool::run(const uint16_t *src, size_t n, uint8_t *dst) {
-    std::unique_lock<std::mutex> lk(p->m);
     p->src = src; p->dst = dst; p->n = n;
     p->orbits.store(0, std::memory_order_relaxed);
-    p->remaining = p->nthreads;
-    ++p->gen;
-    p->cv_go.notify_all();
-    p->cv_done.wait(lk, [&] { return p->remaining == 0; });
+    p->remaining.store(p->nthreads - 1, std::memory_order_relaxed);
+    {
+        std::lock_guard<std::mutex> lk(p->m);                          // pairs with the sleepers' predicate check
+        p->gen.fetch_add(1, std::memory_order_release);
+    }
+    if (p->sleepers.load(std::memory_order_relaxed) > 0) p->cv_go.notify_all();
+    p->slice(0);
+    while (p->remaining.load(std::memory_order_acquire) != 0) _mm_pause();
     return p->orbits.load(std::memory_order_relaxed);
 }
 

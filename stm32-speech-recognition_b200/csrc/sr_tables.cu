@@ -26,20 +26,14 @@ static void build_tables(DevTables &t) {
     for (int j = 1; j <= 12; ++j) bnd[0][j] = cen[2 * j - 1];
     for (int j = 0; j < 12; ++j) bnd[1][j] = cen[2 * j];
     bnd[1][12] = 512;
-    for (int par = 0; par < 2; ++par) {
-        u8 *split = par ? t.split_odd : t.split_even;
-        for (int L = 0; L < 32; ++L) {
-            split[L] = 16;                                   // no boundary: everything in partial sum 0
-            for (int j = 0; j <= 12; ++j)
-                if (bnd[par][j] >= 16 * L && bnd[par][j] <= 16 * L + 16) split[L] = (u8)(bnd[par][j] - 16 * L);
-        }
+    for (int par = 0; par < 2; ++par)
         for (int j = 0; j < 12; ++j) {
             const int h = 2 * j + par, lo = bnd[par][j], hi = bnd[par][j + 1];
-            const int Ll = lo >> 4, Lh = (hi - 1) >> 4;
-            t.seq_lo[h] = (u8)(2 * Ll + ((lo - 16 * Ll) >= split[Ll] ? 1 : 0));
-            t.seq_hi[h] = (u8)(2 * Lh + ((hi - 1 - 16 * Lh) >= split[Lh] ? 1 : 0));
+            auto e_off = [&](int k) { return k >= 512 ? kFltZero : par * kFltRowWords + flt_word(k >> 4, k & 15); };
+            t.flt_lo[h] = (u16)lo; t.flt_hi[h] = (u16)hi;
+            t.flt_e_lo[h] = (u16)e_off(lo); t.flt_e_hi[h] = (u16)e_off(hi);
+            t.flt_x_lo[h] = (u8)(lo >> 4); t.flt_x_hi[h] = (u8)(hi >> 4);   // 512 >> 4 = 32: the grand total
         }
-    }
 }
 
 const DevTables *dev_tables() {
@@ -60,12 +54,14 @@ const DevTables *dev_tables() {
     return ptr[dev];
 }
 
-// host-side copy for unit tests of the filter partition (no GPU needed)
-extern "C" void sr_debug_filter_partition(uint8_t *split_even, uint8_t *split_odd, uint8_t *seq_lo, uint8_t *seq_hi) {
+// host-side copy for unit tests of the filter ranges (no GPU needed): bins [lo[h], hi[h]) per filter, the scratch word
+// offsets the kernel reads for S(lo), S(hi), and the X indices
+extern "C" void sr_debug_filter_ranges(uint16_t *lo, uint16_t *hi, uint16_t *e_lo, uint16_t *e_hi, uint8_t *x_lo, uint8_t *x_hi) {
     DevTables *h = new DevTables;
     build_tables(*h);
-    memcpy(split_even, h->split_even, 32); memcpy(split_odd, h->split_odd, 32);
-    memcpy(seq_lo, h->seq_lo, 24); memcpy(seq_hi, h->seq_hi, 24);
+    memcpy(lo, h->flt_lo, 48); memcpy(hi, h->flt_hi, 48);
+    memcpy(e_lo, h->flt_e_lo, 48); memcpy(e_hi, h->flt_e_hi, 48);
+    memcpy(x_lo, h->flt_x_lo, 24); memcpy(x_hi, h->flt_x_hi, 24);
     delete h;
 }
 

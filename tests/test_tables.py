@@ -77,26 +77,77 @@ def test_log_threshold_table_matches_libm_expression():
         assert o.lib.sro_log100(v) == int(math.log(float(v)) * 100)
 
 
-def test_filter_partition_reproduces_reference_ranges():
-    """the lane-chunk / partial-sum partition used by mfcc_kernel covers exactly the bins of MFCC.C:136-162"""
+def test_filter_ranges_reproduce_reference_ranges():
+    """the filter ranges and prefix-sum read positions used by mfcc_kernel are exactly the bins of MFCC.C:136-162"""
     import sr_b200
     L = sr_b200.lib()
-    se, so = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
-    lo, hi = np.zeros(24, np.uint8), np.zeros(24, np.uint8)
-    L.sr_debug_filter_partition(se.ctypes.data_as(C.c_void_p), so.ctypes.data_as(C.c_void_p),
-                                lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p))
+    lo, hi, elo, ehi = (np.zeros(24, np.uint16) for _ in range(4))
+    xlo, xhi = np.zeros(24, np.uint8), np.zeros(24, np.uint8)
+    L.sr_debug_filter_ranges(*[a.ctypes.data_as(C.c_void_p) for a in (lo, hi, elo, ehi, xlo, xhi)])
     cen, _, _ = gen_tables.tri_tables()
-    # reference ranges
     rng = {0: (0, cen[1]), 23: (cen[22], 512)}
     for h in range(2, 24, 2):
         rng[h] = (cen[h - 1], cen[h + 1])
     for h in range(1, 22, 2):
         rng[h] = (cen[h - 1], cen[h + 1])
+    word = lambda l, i: 16 * l + 4 * ((i >> 2) ^ ((l >> 1) & 3)) + (i & 3)
     for h in range(24):
-        split = so if h & 1 else se
-        bins = []
-        for e in range(int(lo[h]), int(hi[h]) + 1):
-            lane, part = e >> 1, e & 1
-            a, b = (0, int(split[lane])) if part == 0 else (int(split[lane]), 16)
-            bins += [16 * lane + i for i in range(a, b)]
-        assert bins == list(range(*rng[h])), h
+        assert (int(lo[h]), int(hi[h])) == rng[h], h
+        for k, e, x in ((int(lo[h]), int(elo[h]), int(xlo[h])), (int(hi[h]), int(ehi[h]), int(xhi[h]))):
+            assert x == k >> 4
+            assert e == (1150 if k == 512 else (h & 1) * 512 + word(k >> 4, k & 15))
+    # rows never overlap, stay inside the FFT scratch, and the 16-byte stores of 8 neighbouring lanes are conflict-free
+    for q in range(4):
+        for g in range(4):
+            banks = set()
+            for l in range(8 * q, 8 * q + 8):
+                banks |= {(word(l, 4 * g) + c) % 32 for c in range(4)}
+            assert len(banks) == 32
+    used = set()
+    for par in range(2):
+        for l in range(32):
+            for i in range(16):
+                w = par * 512 + word(l, i)
+                assert w not in used and w < 1084
+                used.add(w)
+
+
+def test_prefix_sum_filter_model_equals_direct_sums():
+    """model of mfcc_kernel's filter stage (per-lane running totals + scanned lane totals, a filter = S(hi) - S(lo) read
+    at the offsets of sr_debug_filter_ranges) against the direct sums of MFCC.C:136-162, all mod 2^32"""
+    import sr_b200
+    L = sr_b200.lib()
+    lo, hi, elo, ehi = (np.zeros(24, np.uint16) for _ in range(4))
+    xlo, xhi = np.zeros(24, np.uint8), np.zeros(24, np.uint8)
+    L.sr_debug_filter_ranges(*[a.ctypes.data_as(C.c_void_p) for a in (lo, hi, elo, ehi, xlo, xhi)])
+    cen, tri_odd, tri_even = gen_tables.tri_tables()
+    tri = [np.array(tri_even, np.uint64), np.array(tri_odd, np.uint64)]
+    rng = np.random.default_rng(11)
+    word = lambda l, i: 16 * l + 4 * ((i >> 2) ^ ((l >> 1) & 3)) + (i & 3)
+    M = np.uint64(0xFFFFFFFF)
+    for trial in range(20):
+        E = rng.integers(0, 2 ** 32, 512, dtype=np.uint64)
+        if trial == 0:
+            E[:] = 0xFFFFFFFF
+        fb = np.zeros(1152, np.uint64)
+        X = np.zeros((2, 33), np.uint64)
+        for par in range(2):
+            v = ((E * tri[par]) & M) // np.uint64(100)
+            tot = np.zeros(32, np.uint64)
+            for l in range(32):
+                run = np.uint64(0)
+                for i in range(16):
+                    fb[par * 512 + word(l, i)] = run
+                    run = (run + v[16 * l + i]) & M
+                tot[l] = run
+            inc = np.cumsum(tot) & M
+            X[par, :32] = (inc - tot) & M
+            X[par, 32] = inc[31]
+        for h in range(24):
+            par = h & 1
+            got = ((X[par, xhi[h]] + fb[ehi[h]]) - (X[par, xlo[h]] + fb[elo[h]])) & M
+            a, b = (0, cen[1]) if h == 0 else ((cen[22], 512) if h == 23 else (cen[h - 1], cen[h + 1]))
+            want = np.uint64(0)
+            for k in range(a, b):
+                want = (want + ((E[k] * tri[par][k]) & M) // np.uint64(100)) & M
+            assert got == want, (trial, h)
