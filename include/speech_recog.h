@@ -118,6 +118,17 @@ int         sr_bind_thread_to_device(int device);
 int         sr_device_numa_node(int device);              /* -1 = unknown                            */
 int         sr_host_numa_node(const void *p);             /* node backing the page at p; -1 = unknown */
 
+/* Frame geometry of get_mfcc for this handle (sr_mfcc_batch*, sr_recognise_batch*, sr_enrol_batch, streaming):
+ *   SR_GEOM_REF  160-sample frames / 80 hop / 1024-point FFT -- the reference's (VAD.H:5-8, MFCC.H:8); bit-exact parity
+ *   SR_GEOM_B    200-sample frames / 80 hop /  256-point FFT -- BASELINE configs[0]'s "256-pt/25 ms/10 ms"; an EXTENSION:
+ *                the reference's algorithm and Matlab table formulas at the other two sizes, checked only against this
+ *                repo's own CPU restatement (parity unpinned by the reference). noise_atap / VAD keep the reference's
+ *                framing in both; features of the two geometries must not be mixed in one bank. */
+#define SR_GEOM_REF 0
+#define SR_GEOM_B   1
+int sr_set_geometry(sr_handle *h, int geom);
+int sr_get_geometry(const sr_handle *h);
+
 /* Template bank: n_slot slots of slot_stride bytes (>= sizeof(v_ftr_tag), multiple of 4), each
  * starting with a v_ftr_tag; the flash layout of Flash.H:11-20 is slot_stride = 4096.
  * sr_set_bank copies host->device; sr_set_bank_dev borrows a device pointer. */

@@ -151,6 +151,74 @@ void sro_mfcc(const uint16_t *pcm, uint32_t start, uint32_t end, const sro_atap 
     out->frm_num = frm_con;                                          /* MFCC.C:189 */
 }
 
+/* ---- GEOM_B extension (BASELINE configs[0]: 25 ms frames / 10 ms hop / 256-point FFT) ---------------------------------
+ * get_mfcc (MFCC.C:86-191) with frame_len = 200, fft_point = 256, frq_max = 128 and the tables the reference's Matlab
+ * formulas give for that geometry (tools/gen_tables.py; speech_recog.m:217-313); everything else -- pre-emphasis 95/100,
+ * hamm/1000, magnitude*10, energy, tri/100, log*100, DCT/100 with s16 accumulation, vv_frm_max -- as in MFCC.C.
+ * PARITY UNPINNED: the reference has no 256-point path; this function is the only checker of the CUDA GEOM_B kernel. */
+int sro_cr4_fft(uint32_t *out, const uint32_t *in, unsigned N);          /* cr4_fft_generic.c */
+#define SRO_B_FRAME_LEN 200
+#define SRO_B_FFT_POINT 256
+#define SRO_B_FRQ_MAX 128
+void sro_fft_raw_n(const uint32_t *in, uint32_t *out, uint32_t N) { sro_cr4_fft(out, in, N); }
+void sro_mfcc_geom_b(const uint16_t *pcm, uint32_t start, uint32_t end, const sro_atap *atap, sro_ftr *out) {
+    uint32_t nbytes = (uint32_t)(2u * end) - (uint32_t)(2u * start);
+    uint16_t v_frm_num = (uint16_t)((nbytes / 2u - SRO_B_FRAME_LEN) / SRO_FRAME_MOV + 1u);
+    if (v_frm_num > SRO_VV_FRM_MAX) { out->frm_num = 0; return; }
+    int32_t mid = (int32_t)atap->mid_val;
+    int16_t *mfcc_p = out->mfcc_dat;
+    uint16_t frm_con = 0;
+    for (int64_t p = (int64_t)start; p <= (int64_t)end - SRO_B_FRAME_LEN; p += SRO_FRAME_MOV) {
+        uint32_t in[SRO_B_FFT_POINT], fo[SRO_B_FFT_POINT], mag[SRO_B_FRQ_MAX], pow_spct[SRO_TRI_NUM];
+        for (int i = 0; i < SRO_B_FRAME_LEN; ++i) {
+            int32_t t = ((int32_t)pcm[p + i] - mid) - ((int32_t)pcm[p + i - 1] - mid) * 95 / 100;
+            in[i] = (uint16_t)(int16_t)(t * (int32_t)sr_tab_b_hamm[i] / 1000);
+        }
+        for (int i = SRO_B_FRAME_LEN; i < SRO_B_FFT_POINT; ++i) in[i] = 0;
+        sro_cr4_fft(fo, in, SRO_B_FFT_POINT);
+        for (int i = 0; i < SRO_B_FRQ_MAX; ++i) {
+            int32_t re = (int16_t)(fo[i]), im = (int16_t)(fo[i] >> 16);
+            int32_t pw = (int32_t)((uint32_t)(re * re) + (uint32_t)(im * im));
+            float f = sqrtf((float)pw) * 10;
+            mag[i] = (pw < 0) ? 0u : (uint32_t)f;
+            mag[i] *= mag[i];
+        }
+        const uint16_t *cen = sr_tab_b_tri_cen;
+        pow_spct[0] = 0;
+        for (uint32_t i = 0; i < cen[1]; ++i) pow_spct[0] += mag[i] * sr_tab_b_tri_even[i] / 100u;
+        for (int h = 2; h < SRO_TRI_NUM; h += 2) {
+            pow_spct[h] = 0;
+            for (uint32_t i = cen[h - 1]; i < cen[h + 1]; ++i) pow_spct[h] += mag[i] * sr_tab_b_tri_even[i] / 100u;
+        }
+        for (int h = 1; h < SRO_TRI_NUM - 2; h += 2) {
+            pow_spct[h] = 0;
+            for (uint32_t i = cen[h - 1]; i < cen[h + 1]; ++i) pow_spct[h] += mag[i] * sr_tab_b_tri_odd[i] / 100u;
+        }
+        pow_spct[SRO_TRI_NUM - 1] = 0;
+        for (uint32_t i = cen[SRO_TRI_NUM - 2]; i < SRO_B_FRQ_MAX; ++i)
+            pow_spct[SRO_TRI_NUM - 1] += mag[i] * sr_tab_b_tri_odd[i] / 100u;
+        for (int h = 0; h < SRO_TRI_NUM; ++h) pow_spct[h] = sro_log100(pow_spct[h]);
+        const int8_t *dct = sr_tab_dct;
+        for (int c = 0; c < SRO_MFCC_NUM; ++c) {
+            int16_t acc = 0;
+            for (int i = 0; i < SRO_TRI_NUM; ++i)
+                acc = (int16_t)(acc + ((int32_t)pow_spct[i]) * ((int32_t)dct[i]) / 100);
+            mfcc_p[c] = acc;
+            dct += SRO_TRI_NUM;
+        }
+        mfcc_p += SRO_MFCC_NUM;
+        ++frm_con;
+    }
+    out->frm_num = frm_con;
+}
+void sro_mfcc_geom_b_batch(const uint16_t *pcm, uint32_t U, uint32_t B, const uint32_t *seg2, const sro_atap *atap, sro_ftr *ftr) {
+    for (uint32_t b = 0; b < B; ++b) {
+        const uint32_t st = seg2[2 * b], en = seg2[2 * b + 1];
+        if (st == SRO_NULL || en == SRO_NULL || en > U || st > en || en - st < SRO_B_FRAME_LEN) { ftr[b].frm_num = 0; continue; }
+        sro_mfcc_geom_b(pcm + (size_t)b * U, st, en, atap + b, ftr + b);
+    }
+}
+
 /* ---- DTW.C:45-62 get_dis --------------------------------------------------------------------- */
 uint32_t sro_get_dis(const int16_t *a, const int16_t *b) {
     uint32_t dis = 0;

@@ -108,6 +108,13 @@ int sr_sync(sr_handle *h) {
     return 0;
 }
 
+int sr_set_geometry(sr_handle *h, int geom) {
+    SR_REQUIRE(h, h && (geom == SR_GEOM_REF || geom == SR_GEOM_B));
+    h->geom = geom;
+    return 0;
+}
+int sr_get_geometry(const sr_handle *h) { return h ? h->geom : SR_GEOM_REF; }
+
 uint64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
 
 // ---- pinned host memory -------------------------------------------------------------------------------
@@ -265,7 +272,7 @@ int sr_mfcc_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B,
     SR_REQUIRE(h, h && (B == 0 || (pcm && seg && atap && ftr)));
     SR_REQUIRE(h, seg_stride >= 2 && (reinterpret_cast<uintptr_t>(ftr) & 3) == 0);
     DeviceGuard g(h->device);
-    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, pcm, U, B, seg, seg_stride, atap, ftr)); }
     h->launches += B ? 1 : 0;
     return 0;
 }
@@ -329,7 +336,7 @@ int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32
     // main.c:258-260 noise_atap + VAD (one fused launch on the staged utterance)
     { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, U, 1, 1, atap, seg, h->num_sms, h->stream)); }
     // main.c:268 get_mfcc of segment 0
-    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc(pcm, U, B, seg, 6, atap, ftr, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, pcm, U, B, seg, 6, atap, ftr)); }
     { TimedLaunch tl(h, TAG_STATUS); SR_CK(h, launch_status(seg, ftr, B, status, h->stream)); }
     h->launches += 3;
     // main.c:276-294 template scan, argmin, command index
@@ -668,7 +675,7 @@ int sr_enrol_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, ui
     H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
     SR_CK(h, cudaMemsetAsync(h->atap.p, 0, (size_t)B * sizeof(atap_tag), h->stream));
     { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(static_cast<const u16 *>(h->pcm.p), U, B, n_len, U, 1, 1, static_cast<atap_tag *>(h->atap.p), static_cast<u32 *>(h->seg.p), h->num_sms, h->stream)); }
-    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc(static_cast<const u16 *>(h->pcm.p), U, B, static_cast<const u32 *>(h->seg.p), 6, static_cast<const atap_tag *>(h->atap.p), h->ftr.p, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, static_cast<const u16 *>(h->pcm.p), U, B, static_cast<const u32 *>(h->seg.p), 6, static_cast<const atap_tag *>(h->atap.p), h->ftr.p)); }
     SR_CK(h, launch_status(static_cast<const u32 *>(h->seg.p), h->ftr.p, B, static_cast<u8 *>(h->status.p), h->stream));
     SR_CK(h, launch_pack_slots(h->ftr.p, static_cast<const u8 *>(h->status.p), B, h->misc0.p, slot_stride, h->stream));
     h->launches += 4;

@@ -17,6 +17,8 @@ cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
                         int num_sms, cudaStream_t st, const u32 *row_map = nullptr, u32 rows_total = 0,
                         const u32 *B_dev = nullptr);
+cudaError_t launch_mfcc_geomb(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
+                              int num_sms, cudaStream_t st, const u32 *row_map = nullptr, const u32 *B_dev = nullptr);
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
                                cudaStream_t st);
 cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
@@ -78,6 +80,7 @@ struct sr_handle {
     std::vector<uint8_t> labels;
     u32 n_labels = 0, label_stride = 0;
     sr_comm *comm = nullptr;                           // the exchange step (sr_comm_create), optional
+    int geom = 0;                                      // SR_GEOM_REF (160/80/1024) or SR_GEOM_B (200/80/256, extension)
     int numa_node = -1;                                // node the device hangs off (-1 unknown / single node)
     // grow-only device workspaces
     DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
@@ -108,6 +111,13 @@ inline cudaError_t ensure(DevBuf &b, size_t bytes) {
     if (e != cudaSuccess) { b.p = nullptr; return e; }
     b.cap = want;
     return cudaSuccess;
+}
+
+// get_mfcc in the handle's geometry
+inline cudaError_t launch_mfcc_h(sr_handle *h, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
+                                 void *ftr, const u32 *row_map = nullptr, u32 rows_total = 0, const u32 *B_dev = nullptr) {
+    if (h->geom == 1) return launch_mfcc_geomb(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, B_dev);
+    return launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, rows_total, B_dev);
 }
 
 // records a (start,end) event pair around one kernel launch when timing is enabled

@@ -338,9 +338,8 @@ static int streams_push_impl(sr_stream_pool *p, const uint16_t *chunk, uint32_t 
         static_cast<atap_tag *>(p->atap_ev.p), static_cast<u32 *>(p->map_ev.p), n_ev, p->cap);
     SR_CK(h, cudaGetLastError());
     // recognise the closed segments; every kernel reads the number of events from device memory (upper bound: cap)
-    SR_CK(h, launch_mfcc(static_cast<const u16 *>(p->pcm.p), p->L, p->cap, static_cast<const u32 *>(p->seg_ev.p), 2,
-                         static_cast<const atap_tag *>(p->atap_ev.p), p->ftr.p, h->num_sms, h->stream,
-                         static_cast<const u32 *>(p->map_ev.p), p->S, n_ev));
+    SR_CK(h, launch_mfcc_h(h, static_cast<const u16 *>(p->pcm.p), p->L, p->cap, static_cast<const u32 *>(p->seg_ev.p), 2,
+                           static_cast<const atap_tag *>(p->atap_ev.p), p->ftr.p, static_cast<const u32 *>(p->map_ev.p), p->S, n_ev));
     SR_CK(h, ensure(h->best, (size_t)p->cap * 8));
     u64 *best = static_cast<u64 *>(h->best.p);
     const u32 gb = (p->cap + 255) / 256;

@@ -34,6 +34,14 @@ static void build_tables(DevTables &t) {
             t.flt_e_lo[h] = (u16)e_off(lo); t.flt_e_hi[h] = (u16)e_off(hi);
             t.flt_x_lo[h] = (u8)(lo >> 4); t.flt_x_hi[h] = (u8)(hi >> 4);   // 512 >> 4 = 32: the grand total
         }
+    // GEOM_B extension: same construction over 128 bins (MFCC.C:136-162 with the regenerated centres)
+    for (int i = 0; i < 200; ++i) t.b_hamm[i] = sr_tab_b_hamm[i];
+    for (int i = 0; i < 128; ++i) { t.b_tri_even[i] = sr_tab_b_tri_even[i]; t.b_tri_odd[i] = sr_tab_b_tri_odd[i]; }
+    const uint16_t *cb = sr_tab_b_tri_cen;
+    for (int h = 0; h < 24; ++h) {
+        t.b_flt_lo[h] = (u16)(h == 0 ? 0 : cb[h - 1]);
+        t.b_flt_hi[h] = (u16)(h == 23 ? 128 : cb[h + 1]);
+    }
 }
 
 const DevTables *dev_tables() {

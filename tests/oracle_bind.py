@@ -86,6 +86,20 @@ class PortOracle(_Base):
         self.lib.sro_mfcc_batch(_p(pcm), C.c_uint32(U), C.c_uint32(B), _p(seg2), _p(atap), _p(ftr), C.c_int(nthreads))
         return ftr
 
+    def mfcc_geom_b_batch(self, pcm, seg2, atap):
+        """GEOM_B extension (200/80/256): this repo's own restatement is its only checker (parity unpinned)"""
+        B, U = pcm.shape
+        ftr = np.zeros(B, FTR_DTYPE)
+        seg2 = np.ascontiguousarray(seg2, np.uint32).reshape(B, 2)
+        self.lib.sro_mfcc_geom_b_batch(_p(pcm), C.c_uint32(U), C.c_uint32(B), _p(seg2), _p(atap), _p(ftr))
+        return ftr
+
+    def fft_raw_n(self, packed, N):
+        out = np.zeros_like(packed)
+        for i in range(packed.shape[0]):
+            self.lib.sro_fft_raw_n(_p(packed[i]), _p(out[i]), C.c_uint32(N))
+        return out
+
     def get_dis(self, a, b):
         return np.array([self.lib.sro_get_dis(_p(a[i]), _p(b[i])) for i in range(a.shape[0])], np.uint32)
 

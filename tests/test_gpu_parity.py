@@ -735,6 +735,59 @@ def test_stream_group_shards_streams_over_handles(handle, ora):
         h.close()
 
 
+def test_geom_b_extension_vs_own_oracle():
+    """GEOM_B (200/80/256, BASELINE configs[0]'s framing): PARITY UNPINNED -- the reference has no 256-point path, the
+    checker is this repo's own restatement (oracle/sr_oracle.c::sro_mfcc_geom_b, whose FFT generalisation is pinned at
+    N = 1024). get_mfcc alone on synthetic / full-range / ragged segments, then the whole recognise path"""
+    po = ob.port()
+    h = sr_b200.Handle(0)
+    h.set_geometry(1)
+    B, U = 96, 8000
+    pcm = sr_b200.synth_pcm_host(B, U, 0xB0B0)
+    rng = np.random.default_rng(0xB)
+    pcm[80:] = rng.integers(0, 65536, (16, U)).astype(np.uint16)          # full-range samples: s16 / u32 wraps
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = 2048
+    atap["mid_val"][80:] = rng.integers(0, 65536, 16)
+    seg = np.zeros((B, 2), np.uint32)
+    seg[:, 0] = 80 * rng.integers(1, 30, B)
+    seg[:, 1] = np.minimum(seg[:, 0] + 80 * rng.integers(1, 100, B), U)
+    seg[1] = (80, 80 + 199)                                                # shorter than one 200-sample frame
+    seg[2] = (80, 280)                                                     # exactly one frame
+    seg[3] = (80, 80 + 200 + 80 * 119)                                     # 120 frames: rejected (vv_frm_max)
+    seg[4] = (0xFFFFFFFF, 0xFFFFFFFF)
+    seg[5] = (160, 8000)
+    got = h.mfcc(pcm, seg, atap)
+    want = po.mfcc_geom_b_batch(pcm, seg, atap)
+    assert ob.ftr_equal(got, want)
+    assert int(got["frm_num"][2]) == 1 and int(got["frm_num"][1]) == 0 and int(got["frm_num"][3]) == 0 and int(got["frm_num"][5]) == 96
+    assert (got["frm_num"] > 0).sum() > 60
+    # the same frames in the reference geometry are different numbers (this is a different front end, not a re-labelling)
+    h.set_geometry(0)
+    ref_geom = h.mfcc(pcm, seg, atap)
+    assert not ob.ftr_equal(ref_geom, got)
+    # whole path: enrol + recognise in GEOM_B == VAD (reference framing) -> GEOM_B features -> dtw -> argmin on the CPU
+    h.set_geometry(1)
+    T = 6
+    tpl = sr_b200.synth_pcm_host(T, U, 0x7E3A0000)
+    bank, est = h.enrol(tpl, 2400)
+    assert (est == 0).all()
+    h.set_bank(bank, T, 4096)
+    utt = sr_b200.synth_pcm_host(32, U, 0x5EED0000)
+    out = h.recognise(utt, 2400)
+    a = np.zeros(32, sr_b200.ATAP_DTYPE)
+    for b in range(32):
+        a[b] = po.noise_atap(utt[b], 2400)[0]
+    sg = np.stack([po.vad(utt[b], U, a[b:b + 1]) for b in range(32)]).reshape(32, 3, 2)
+    assert np.array_equal(out["seg_off"], sg)
+    f = po.mfcc_geom_b_batch(utt, sg[:, 0, :], a)
+    ok = sg[:, 0, 1] != ob.NULL
+    assert ob.ftr_equal(out["ftr"][ok], f[ok])
+    sc, _ = po.dtw_batch(f, bank, T, 4096, check_sign=1)
+    assert np.array_equal(out["score"][ok], sc[ok]) and ok.sum() >= 30
+    h.close()
+
+
 def test_recognise_multi_handle_sharding(ora):
     """sr_recognise_batch_multi: contiguous shards over several handles (all visible GPUs, or two handles on one GPU)
     == the single-handle result, bit for bit"""

@@ -125,3 +125,32 @@ def test_dtw_band_oracle_properties():
     wide, _ = o.dtw_batch(ftr, raw, 6, 2860, band_r=200)
     ok = (sc != ob.NULL) & (wide != ob.NULL)
     assert (wide[ok] <= sc[ok]).all()                               # a wider band can only lower the DP optimum
+
+
+def test_generic_radix4_fft_reproduces_the_1024_point_restatement():
+    """oracle/cr4_fft_generic.c (the asm's algorithm for N = 64 / 256 / 1024) at N = 1024 == the register-level
+    restatement of cr4_fft_1024_stm32.s -- and, where the reference is compiled, == libref's FFT: this pins the
+    generalisation whose N = 256 instance carries the GEOM_B extension"""
+    import oracle_bind as ob
+    rng = np.random.default_rng(256)
+    x = rng.integers(0, 2 ** 32, (24, 1024), dtype=np.uint64).astype(np.uint32)
+    x[0] = 0x80008000
+    x[1] = 0x7FFF7FFF
+    x[2, :160] = rng.integers(0, 65536, 160).astype(np.uint32)
+    x[2, 160:] = 0
+    po = ob.port()
+    want = po.fft_raw(x)
+    assert np.array_equal(po.fft_raw_n(x, 1024), want)
+    if ob.have_ref():
+        assert np.array_equal(ob.ref().fft_raw(x), want)
+    # smaller sizes: DC and single-tone sanity (|error| vs the exact DFT/N stays within a few LSB like the 1024-point routine)
+    for N in (64, 256):
+        n = np.arange(N)
+        tone = np.round(8000 * np.cos(2 * np.pi * 5 * n / N)).astype(np.int64)
+        packed = (tone & 0xFFFF).astype(np.uint32).reshape(1, N)
+        out = po.fft_raw_n(packed, N)[0]
+        re = (out & 0xFFFF).astype(np.int16).astype(np.int64)
+        im = (out >> 16).astype(np.int16).astype(np.int64)
+        exact = np.fft.fft(tone) / N
+        assert np.abs(re - exact.real).max() <= 8 and np.abs(im - exact.imag).max() <= 8
+        assert abs(re[5] - 4000) <= 8 and abs(re[N - 5] - 4000) <= 8

@@ -34,9 +34,16 @@ def mround(x):
     return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
 
 
-def hamm_table():
-    return [mround(10000 * (0.54 - 0.46 * math.cos(2 * math.pi * i / (FRAME_LEN - 1))))
-            for i in range(FRAME_LEN)]
+# GEOM_B (BASELINE configs[0]: 25 ms frames, 10 ms hop, 256-point FFT): an EXTENSION -- the reference only ships the
+# 160/80/1024 geometry; the same Matlab formulas are evaluated with frame_len = 200 and fft_point = 256
+FRAME_LEN_B = 200
+FFT_POINT_B = 256
+FRQ_MAX_B = FFT_POINT_B // 2
+
+
+def hamm_table(frame_len=FRAME_LEN):
+    return [mround(10000 * (0.54 - 0.46 * math.cos(2 * math.pi * i / (frame_len - 1))))
+            for i in range(frame_len)]
 
 
 def dct_table():
@@ -44,7 +51,8 @@ def dct_table():
             for c in range(MFCC_NUM) for h in range(TRI_NUM)]
 
 
-def tri_tables():
+def tri_tables(frq_max=FRQ_MAX):
+    FRQ_MAX = frq_max
     f_max = FS / 2
     mel_max = 2595 * math.log10(1 + f_max / 700)
     mel_step = mel_max / (TRI_NUM + 1)
@@ -124,6 +132,7 @@ def main():
     here = os.path.dirname(os.path.abspath(__file__))
     dst = os.path.join(here, "..", "stm32-speech-recognition_b200", "csrc", "sr_tables.h")
     cen, odd, even = tri_tables()
+    cen_b, odd_b, even_b = tri_tables(FRQ_MAX_B)
     thr, lmax = log_thresholds()
     parts = [
         "// GENERATED by tools/gen_tables.py -- do not edit. Closed-form tables of the MFCC path;",
@@ -138,6 +147,11 @@ def main():
         c_array("uint16_t", "sr_tab_tri_odd", odd),
         c_array("uint16_t", "sr_tab_tri_even", even),
         c_array("int8_t", "sr_tab_dct", dct_table(), 24),
+        "/* GEOM_B (200/80/256): extension, no counterpart in the reference's headers */",
+        c_array("uint16_t", "sr_tab_b_hamm", hamm_table(FRAME_LEN_B)),
+        c_array("uint16_t", "sr_tab_b_tri_cen", cen_b),
+        c_array("uint16_t", "sr_tab_b_tri_odd", odd_b),
+        c_array("uint16_t", "sr_tab_b_tri_even", even_b),
         c_array("int16_t", "sr_tab_twiddle", twiddle_table(), 12),
         c_array("uint32_t", "sr_tab_log_thr", thr + [2 ** 32 - 1], 8),
         "#endif",
