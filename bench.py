@@ -277,6 +277,7 @@ def run_kernel_workload(args):
     torch.cuda.set_stream(stream)
     h = sr_b200.Handle(0)
     h.set_stream(stream.cuda_stream)
+    h.set_dtw_variant(args.dtw_variant)
     B = args.batch
     cores = args.ref_procs if args.ref_procs > 0 else usable_cores()
     peak, peak_src = peaks()
@@ -387,6 +388,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="recognise", choices=["recognise", "mfcc", "dtw", "dtw_band", "stream"])
     ap.add_argument("--streams", type=int, default=8192)
+    ap.add_argument("--dtw-variant", type=int, default=-1, help="greedy dtw kernel: 0 static, 1 dynamic pair scheduling, -1 library default")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3], help="1 = BASELINE configs[1] per GPU (default); 3 = configs[3]: 131072 utterances per GPU x 50 templates")
     ap.add_argument("--no-config3", action="store_true", help="multi-GPU runs: skip the appended configs[3] pass")
     ap.add_argument("--no-stream", action="store_true", help="skip the appended configs[4] streaming pass")
@@ -427,6 +429,7 @@ def main():
     torch.cuda.set_stream(stream)
     h = sr_b200.Handle(local)
     h.set_stream(stream.cuda_stream)
+    h.set_dtw_variant(args.dtw_variant)
     if world > 1:                                   # the exchange step lives behind the C-ABI (sr_comm_*): NCCL id via torch
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:

@@ -313,6 +313,11 @@ int sr_debug_unpack12(sr_handle *h, const uint8_t *packed, uint64_t n, uint16_t 
 int sr_timing_enable(sr_handle *h, uint32_t max_records);
 int sr_timing_collect(sr_handle *h, uint32_t *tags, float *ms, uint32_t cap, uint32_t *n);
 
+/* Kernel variant of the greedy dtw (both bit-identical): 0 = one lane per (utterance, template) pair for the whole walk,
+ * 1 = pairs handed to lanes dynamically from a ring of staged utterances (no lane waits for the longest walk of its
+ * warp), -1 = the library default (SR_DTW_VARIANT=0|1 overrides it). */
+int sr_set_dtw_variant(sr_handle *h, int variant);
+
 /* number of kernel launches this handle has issued (bench.py reports it as gpu_launches) */
 uint64_t sr_launch_count(const sr_handle *h);
 

@@ -78,7 +78,7 @@ int sr_destroy(sr_handle *h) {
     delete h->pool;
     for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
     DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
-                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2};
+                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2, &h->dtw_scratch};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -114,6 +114,12 @@ int sr_set_geometry(sr_handle *h, int geom) {
     return 0;
 }
 int sr_get_geometry(const sr_handle *h) { return h ? h->geom : SR_GEOM_REF; }
+
+int sr_set_dtw_variant(sr_handle *h, int variant) {
+    SR_REQUIRE(h, h && variant >= -1 && variant <= 1);
+    h->dtw_variant = variant;
+    return 0;
+}
 
 uint64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
 
@@ -297,7 +303,7 @@ static int dtw_dev_impl(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t 
             SR_CK(h, launch_dtw_band(in, B, h->bank, h->n_slot, h->slot_stride, flags, band_r, score, best, h->num_sms, h->stream));
         } else {
             TimedLaunch tl(h, TAG_DTW);
-            SR_CK(h, launch_dtw(in, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream));
+            SR_CK(h, launch_dtw_h(h, in, B, flags, score, best, status));
         }
         ++h->launches;
     }

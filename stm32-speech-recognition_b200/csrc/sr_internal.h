@@ -23,6 +23,9 @@ cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len,
                                cudaStream_t st);
 cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
                        u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev = nullptr);
+cudaError_t launch_dtw_dyn(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
+                           u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 *max_frm_scratch,
+                           const u32 *B_dev = nullptr);
 cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, int band_r,
                             u32 *score, u64 *best, int num_sms, cudaStream_t st);
 cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st);
@@ -80,6 +83,8 @@ struct sr_handle {
     std::vector<uint8_t> labels;
     u32 n_labels = 0, label_stride = 0;
     sr_comm *comm = nullptr;                           // the exchange step (sr_comm_create), optional
+    int dtw_variant = -1;                              // greedy dtw kernel: 0 static lane = pair (sr_dtw.cu), 1 dynamic pairs (sr_dtw_dyn.cu), -1 default
+    DevBuf dtw_scratch;                                // one word: max frm_num of the current inputs (dynamic kernel's slot size)
     int geom = 0;                                      // SR_GEOM_REF (160/80/1024) or SR_GEOM_B (200/80/256, extension)
     int numa_node = -1;                                // node the device hangs off (-1 unknown / single node)
     // grow-only device workspaces
@@ -118,6 +123,26 @@ inline cudaError_t launch_mfcc_h(sr_handle *h, const u16 *pcm, u32 U, u32 B, con
                                  void *ftr, const u32 *row_map = nullptr, u32 rows_total = 0, const u32 *B_dev = nullptr) {
     if (h->geom == 1) return launch_mfcc_geomb(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, B_dev);
     return launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, rows_total, B_dev);
+}
+
+// greedy dtw of B inputs against the handle's bank with the handle's kernel variant
+#ifndef SR_DTW_VARIANT_DEFAULT
+#define SR_DTW_VARIANT_DEFAULT 0
+#endif
+inline cudaError_t launch_dtw_h(sr_handle *h, const void *in_ftr, u32 B, u32 flags, u32 *score, u64 *best, const u8 *status,
+                                const u32 *B_dev = nullptr) {
+    int v = h->dtw_variant;
+    if (v < 0) {
+        static const int env_v = [] { const char *e = getenv("SR_DTW_VARIANT"); return e && *e ? atoi(e) : SR_DTW_VARIANT_DEFAULT; }();
+        v = env_v;
+    }
+    if (v == 1) {
+        cudaError_t e = ensure(h->dtw_scratch, 16);
+        if (e != cudaSuccess) return e;
+        return launch_dtw_dyn(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream,
+                              static_cast<u32 *>(h->dtw_scratch.p), B_dev);
+    }
+    return launch_dtw(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream, B_dev);
 }
 
 // records a (start,end) event pair around one kernel launch when timing is enabled

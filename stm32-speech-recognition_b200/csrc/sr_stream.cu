@@ -347,8 +347,7 @@ static int streams_push_impl(sr_stream_pool *p, const uint16_t *chunk, uint32_t 
                                                    static_cast<u8 *>(p->status.p), static_cast<u32 *>(p->frm.p), best);
     SR_CK(h, cudaGetLastError());
     if (h->n_slot)
-        SR_CK(h, launch_dtw(p->ftr.p, p->cap, h->bank, h->n_slot, h->slot_stride, SR_DTW_CHECK_SIGN, nullptr, best,
-                            static_cast<const u8 *>(p->status.p), h->num_sms, h->stream, n_ev));
+        SR_CK(h, launch_dtw_h(h, p->ftr.p, p->cap, SR_DTW_CHECK_SIGN, nullptr, best, static_cast<const u8 *>(p->status.p), n_ev));
     u32 *out_count = static_cast<u32 *>(p->out.p);
     sr_stream_event *out_rec = reinterpret_cast<sr_stream_event *>(static_cast<unsigned char *>(p->out.p) + 16);
     stream_finish_kernel<<<gb, 256, 0, h->stream>>>(static_cast<const StreamEventDev *>(p->ev.p), n_ev, p->cap,

@@ -97,6 +97,7 @@ def lib():
         L.sr_comm_wait.argtypes = [vp]
         L.sr_allgather_dev.argtypes = [vp, vp, vp, C.c_size_t]
         L.sr_recognise_batch_dev_allgather.argtypes = [vp, vp, u32, u32, u32, C.POINTER(RecogOut), vp, vp]
+        L.sr_set_dtw_variant.argtypes = [vp, i32]
         L.sr_set_geometry.argtypes = [vp, i32]
         L.sr_get_geometry.argtypes = [vp]
         L.sr_set_labels.argtypes = [vp, vp, u32, u32]
@@ -343,6 +344,10 @@ class Handle:
                         ("atap", "seg_off", "ftr", "score", "best_idx", "best_dis", "cmd", "status")])
         self._ck(lib().sr_recognise_batch_dev_allgather(self._h, _p(pcm_ptr), U, B, n_len, C.byref(ro),
                                                          _p(gathered_score), _p(gathered_best)))
+
+    def set_dtw_variant(self, v):
+        """greedy dtw kernel: 0 static lane = pair, 1 dynamic pair scheduling, -1 library default"""
+        self._ck(lib().sr_set_dtw_variant(self._h, int(v)))
 
     def set_geometry(self, geom):
         """0 = reference 160/80/1024, 1 = GEOM_B 200/80/256 (extension, parity unpinned)"""

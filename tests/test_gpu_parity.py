@@ -377,6 +377,53 @@ def test_dtw_empty_feature_sets_are_deterministic(handle, ora):
         handle.dtw(sr_b200.synth_ftr_host(64, 0xE1, 90, 119).view(sr_b200.FTR_DTYPE).reshape(-1))
 
 
+@pytest.mark.parametrize("T,B,fr", [(1, 70, (1, 119)), (5, 333, (20, 45)), (20, 1500, (23, 43)), (32, 257, (50, 100)),
+                                    (33, 640, (1, 119)), (70, 200, (30, 119)), (200, 300, (50, 100))])
+def test_dtw_dynamic_pair_scheduling_equals_static_and_reference(ora, T, B, fr):
+    """sr_dtw_dyn.cu (pairs pulled dynamically from a ring of staged utterances) == the static kernel == the reference's
+    dtw, scores and first-wins argmin, over bank widths around the 32-template tile, all frame counts, mixed save_sign,
+    the 2:1 guard, garbage headers; run twice so the second launch sees a dirty ring"""
+    h = sr_b200.Handle(0)
+    fin = sr_b200.synth_ftr_host(B, 0xD100 + T, fr[0], fr[1]).view(sr_b200.FTR_DTYPE).reshape(-1).copy()
+    bank = sr_b200.synth_ftr_host(T, 0xD200 + T, fr[0], fr[1], stride=4096)
+    rng = np.random.default_rng(T)
+    bad = rng.random(T) < 0.2
+    bank[bad, 0:2] = 0xFF
+    if T > 3:
+        bank[2, 2:4] = (200, 0)                            # frm_num 200 > vv_frm_max: never walked
+        fin["frm_num"][1] = 0
+        fin["frm_num"][2] = 300
+    h.set_bank(bank, T, 4096)
+    res = {}
+    for v in (0, 1, 1):
+        h.set_dtw_variant(v)
+        res[v] = h.dtw(fin, flags=sr_b200.DTW_CHECK_SIGN)
+        assert all(np.array_equal(a, b) for a, b in zip(res[v], res[0])), v
+    ok = fin["frm_num"] <= 119
+    want, _ = ora.dtw_batch(fin[ok], bank, T, 4096, check_sign=1)
+    valid = np.ones(T, bool)
+    if T > 3:
+        valid[2] = False                                   # the reference would read past the struct: not comparable
+    assert np.array_equal(res[1][0][ok][:, valid], want[:, valid])
+    # through the recognise path (status gate: failed utterances never reach dtw)
+    U = 8000
+    pcm = sr_b200.synth_pcm_host(128, U, 0x77)
+    pcm[::7] = 2048
+    tb, _ = h.enrol(sr_b200.synth_pcm_host(min(T, 24), U, 0x7E3A0000), 2400)
+    h.set_bank(tb, tb.shape[0], 4096)
+    h.set_dtw_variant(0)
+    a = h.recognise(pcm, 2400)
+    h.set_dtw_variant(1)
+    b = h.recognise(pcm, 2400)
+    for k in ("score", "best_idx", "best_dis", "cmd", "status"):
+        if k == "score":
+            okr = a["status"] == 0
+            assert np.array_equal(a[k][okr], b[k][okr])
+        else:
+            assert np.array_equal(a[k], b[k]), k
+    h.close()
+
+
 def test_dtw_extreme_values_wrap(handle, ora):
     """|dif| up to 65535 per dimension: the u32 accumulation of get_dis wraps (DTW.C:56)"""
     rng = np.random.default_rng(2)

@@ -14,3 +14,7 @@ python bench.py --workload dtw --steps 10 > gpurun_out/r2a/dtw.json 2> gpurun_ou
 python bench.py --workload mfcc --steps 10 > gpurun_out/r2a/mfcc.json 2> gpurun_out/r2a/mfcc.err
 grep -h -o '"e2e": {[^}]*}[^}]*}' gpurun_out/r2a/*.json
 grep -h -o '"kernel_ms": {[^}]*}' gpurun_out/r2a/default.json
+python bench.py --workload dtw --steps 10 --dtw-variant 1 > gpurun_out/r2a/dtw_dyn.json 2> gpurun_out/r2a/dtw_dyn.err
+python bench.py --steps 20 --warmup 3 --no-cpu --no-stream --dtw-variant 1 > gpurun_out/r2a/default_dyn.json 2> gpurun_out/r2a/default_dyn.err
+grep -h -o '"kernel_ms": {[^}]*}' gpurun_out/r2a/default_dyn.json
+grep -h -o '"value": [0-9.e+]*' gpurun_out/r2a/dtw.json gpurun_out/r2a/dtw_dyn.json
