@@ -112,6 +112,7 @@ __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid
     const u16 *p = v.x + i0;
     if (mid <= 0xFFFFu) {
         u32 gA[3] = {0, 0, 0}, gB[3] = {0, 0, 0};      // "s >= a_thl", "s >= b_thl"; samples 0..31, 32..63, 64..79
+        u32 bsx = 0, bsn = 0;
         const u32 mid2 = mid | (mid << 16), na = 0u - (a_thl << 16), nb = 0u - (b_thl << 16);
 #pragma unroll
         for (int c = 0; c < 10; ++c) {
@@ -129,7 +130,8 @@ __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid
                 u32 mx, mn;
                 asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(w[j]), "r"(mid2));
                 asm("min.u16x2 %0, %1, %2;" : "=r"(mn) : "r"(w[j]), "r"(mid2));
-                bs = __dp2a_lo(mx - mn, 0x0101u, bs);                       // VAD.C:126-129
+                bsx = __dp2a_lo(mx, 0x0101u, bsx);                          // VAD.C:126-129: sum |x-mid| = sum max - sum min; two
+                bsn = __dp2a_lo(mn, 0x0101u, bsn);                          // IDP.2A (FMA pipe) instead of a subtract on the busy ALU pipe
                 asm("{\n .reg .u32 t, l;\n shl.b32 l, %2, 16;\n"
                     " add.cc.u32 t, l, %3;\n madc.lo.u32 %0, %0, 2, 0;\n"  // VAD.C:134-141 / 143-156, low sample
                     " add.cc.u32 t, l, %4;\n madc.lo.u32 %1, %1, 2, 0;\n"
@@ -139,6 +141,7 @@ __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid
                     : "r"(w[j]), "r"(na), "r"(nb));
             }
         }
+        bs = bsx - bsn;
         H[0] = __brev(gA[0]); H[1] = __brev(gA[1]); H[2] = __brev(gA[2]) >> 16;
         L[0] = ~__brev(gB[0]); L[1] = ~__brev(gB[1]); L[2] = ~(__brev(gB[2]) >> 16) & 0xFFFFu;
         if (a_thl == 0) { H[0] = 0xFFFFFFFFu; H[1] = 0xFFFFFFFFu; H[2] = 0xFFFFu; }   // s >= 0 always
