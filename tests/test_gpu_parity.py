@@ -912,6 +912,65 @@ def test_packed_transport_equals_plain(handle, ora):
     _cmp_recog({k: v[sel] for k, v in packed.items()}, ref)
 
 
+def test_packed_transport_under_torchrun_two_ranks():
+    """the 12-bit transport with two ranks of one node sharing the CPU quota (LOCAL_WORLD_SIZE = 2: each rank sizes its
+    packer pool from its share): packed == plain == device path on every rank"""
+    import subprocess
+    import sys
+    import torch
+    script = os.path.join(HERE, "_torchrun_pack.py")
+    port = 29500 + (os.getpid() % 500)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("rank ok") == 2, r.stdout[-3000:]
+
+
+def test_multi_gpu_c_host_nccl_allgather():
+    """host/spch_host_mgpu.c: plain C + pthreads, one rank per GPU, NCCL all-gather through the C-ABI
+    (sr_recognise_batch_dev_allgather); every rank's gathered scores and argmin keys == the single-GPU batch result"""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (NCCL refuses two ranks on one device)")
+    exe = os.path.join(os.path.dirname(HERE), "stm32-speech-recognition_b200", "host", "spch_host_mgpu")
+    assert os.path.exists(exe), "host binary not built (see __graft_entry__.build)"
+    n = min(torch.cuda.device_count(), 8)
+    r = subprocess.run([exe, str(n), "384"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and ": 0 mismatches" in r.stdout, r.stdout[-2000:]
+
+
+def test_nccl_allgather_through_python_binding_two_ranks():
+    """sr_comm_* from two processes (torchrun): the id travels through torch.distributed, the gather runs inside
+    libspeech_b200.so; gathered block r on every rank == rank r's own results"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = os.path.join(HERE, "_torchrun_comm.py")
+    port = 29500 + ((os.getpid() + 7) % 500)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("rank ok") == 2, r.stdout[-3000:]
+
+
+def test_numa_helpers_and_labels(handle):
+    """placement helpers never fail on a single-node box and report consistently; commstr labels (main.c:25-31, 295)"""
+    L = sr_b200.lib()
+    node = L.sr_device_numa_node(0)
+    arr, p = sr_b200.host_alloc_dev(0, 1 << 20)
+    arr[:] = 7
+    got = L.sr_host_numa_node(C.c_void_p(p))
+    assert node < 0 or got < 0 or got == node
+    sr_b200.host_free(p)
+    assert handle.label(0) == b"0 " and handle.label(9) == b"9 " and handle.label(10) == bytes([0xC9, 0xCF]) and handle.label(18) is None
+    h2 = sr_b200.Handle(0)
+    h2.set_labels([b"on", b"off", b"up"], 4)
+    assert h2.label(1) == b"off" and h2.label(3) is None
+    h2.close()
+
+
 def test_empty_batch_and_argument_errors(handle):
     z = np.zeros((0, 8000), np.uint16)
     assert handle.recognise(z, 2400)["cmd"].shape == (0,)
