@@ -1,3 +1,5 @@
+// sr_mfcc_r1.cu -- the ROUND-1 form of K1 (split-capture filter bank), kept only as the A/B baseline of the filter-stage
+// experiments (SR_MFCC_FILT=0); not on any default path.
 // sr_mfcc.cu -- K1: batched get_mfcc (Src/Speech_Recog/MFCC.C:86-191) with the bit-exact
 // fixed-point radix-4 FFT of Src/BSP/cr4_fft_1024_stm32.s:95-281 done in registers/shared memory.
 //
@@ -35,22 +37,21 @@
 #endif
 
 namespace srk {
-
-cudaError_t launch_mfcc_r1(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
-                           void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total);   // sr_mfcc_r1.cu
+namespace r1 {
 
 constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
-constexpr int kFftWords = kFftWordsTotal;    // FFT data: 1024 + 4 words per 64; filter-stage scratch behind it (sr_common.cuh)
+constexpr int kFftWordsR1 = 1024 + 64;         // +4 words per 64
 
 template <int kConsumerWarps, int kNBuf>
 struct __align__(16) MfccSmem {
     unsigned char pcm[kNBuf][kPcmBufBytes];
     int2 tw[340 * 3];
     u32 log_thr[2220];
-    u32 tri_even[512];                       // filter weights as 32-bit words: no unpacking in the frame loop
-    u32 tri_odd[512];
-    u32 fftbuf[kConsumerWarps][kFftWords];
+    u16 tri_even[512];
+    u16 tri_odd[512];
+    u32 fftbuf[kConsumerWarps][kFftWordsR1];
     s32 wq[kConsumerWarps][160];
+    u32 seq[kConsumerWarps][2][64];
     u32 lg[kConsumerWarps][32];
     u64 full[kNBuf];
     u64 empty[kNBuf];
@@ -149,14 +150,12 @@ __device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> 
 // kSelf = false: warp kConsumerWarps is a dedicated producer. kSelf = true: every warp is a consumer and the staging
 // of utterance it+kAhead is a side job of warp it % kConsumerWarps at the top of iteration it, so all four
 // schedulers of the SM carry the same number of working warps.
-template <int kConsumerWarps, int kNBuf, bool kSelf, int kFilt>
+template <int kConsumerWarps, int kNBuf, bool kSelf>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
                                           unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
-                                          const u32 *__restrict__ row_map, u32 rows_total, const u32 *__restrict__ B_dev) {
-    constexpr int kAhead = kNBuf - 2;
-    if (B_dev) B = min(B, *B_dev);                         // batch size produced on the device (streaming: segments closed by this push)
-    if (blockIdx.x >= B) return;                      // slot of it+kAhead was last used by utterance it-2
+                                          const u32 *__restrict__ row_map, u32 rows_total) {
+    constexpr int kAhead = kNBuf - 2;                      // slot of it+kAhead was last used by utterance it-2
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MfccSmem<kConsumerWarps, kNBuf> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps, kNBuf> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,7 +164,6 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     for (int i = threadIdx.x; i < 340 * 3; i += blockDim.x) sm.tw[i] = tab->tw[i];
     for (int i = threadIdx.x; i < 2220; i += blockDim.x) sm.log_thr[i] = tab->log_thr[i];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) { sm.tri_even[i] = tab->tri_even[i]; sm.tri_odd[i] = tab->tri_odd[i]; }
-    for (int i = threadIdx.x; i < kConsumerWarps; i += blockDim.x) sm.fftbuf[i][kFltZero] = 0u;   // S(512)'s in-lane part
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNBuf; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
         mbar_fence_init();
@@ -201,13 +199,9 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     const int2 k1_2 = sm.tw[q1 * 3 + 1], k1_1 = sm.tw[q1 * 3 + 2];
     const u32 hm0 = tab->hamm[lane], hm1 = tab->hamm[lane + 32], hm2 = tab->hamm[lane + 64],
               hm3 = tab->hamm[lane + 96], hm4 = tab->hamm[lane + 128];
-    // filter role: lanes 0..23 -> filter h = lane: S(hi) - S(lo) of its parity's prefix sums (see DevTables)
-    const int fsw = (lane >> 1) & 3;                       // bank swizzle of the running-total rows (flt_word)
-    int fe_lo = kFltZero, fe_hi = kFltZero, fx_lo = kFltX, fx_hi = kFltX;
-    if (lane < 24) {
-        fe_lo = tab->flt_e_lo[lane]; fe_hi = tab->flt_e_hi[lane];
-        fx_lo = kFltX + (lane & 1) * 33 + tab->flt_x_lo[lane]; fx_hi = kFltX + (lane & 1) * 33 + tab->flt_x_hi[lane];
-    }
+    const int sp_e = tab->split_even[lane], sp_o = tab->split_odd[lane];
+    int flo = 0, fhi = -1, fpar = 0;
+    if (lane < 24) { flo = tab->seq_lo[lane]; fhi = tab->seq_hi[lane]; fpar = lane & 1; }
     // DCT role: lanes 0..23 -> coefficient c = lane>>1, half = lane&1 (12 filters each)
     s32 dctk[12];
 #pragma unroll
@@ -336,58 +330,39 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
             __syncwarp();
 
             // ---- triangular filters, MFCC.C:136-162: lane owns bins [16*lane, 16*lane+16) ------
-            // acc[h] = sum over the filter's bins of (E[k]*tri[k])/100, u32 wrap. Per parity the per-bin terms become
-            // prefix sums: a lane keeps the running totals of its 16 bins (written to the warp's scratch), the lane
-            // totals are scanned over the warp, and a filter is a difference of two prefix values -- exact mod 2^32.
             {
                 u32 E[16];
                 const uint4 *e4 = reinterpret_cast<const uint4 *>(fb + 16 * lane + 4 * (lane >> 2));   // padF(16*lane)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const uint4 v = e4[j]; E[4 * j] = v.x; E[4 * j + 1] = v.y; E[4 * j + 2] = v.z; E[4 * j + 3] = v.w; }
-                __syncwarp();                                               // every lane holds its energies: fb is scratch now
-                const uint4 *we4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
-                const uint4 *wo4 = reinterpret_cast<const uint4 *>(sm.tri_odd + 16 * lane);
-                uint4 *re4 = reinterpret_cast<uint4 *>(fb + 16 * lane);                    // this lane's row, group g at slot g ^ fsw
-                uint4 *ro4 = reinterpret_cast<uint4 *>(fb + kFltRowWords + 16 * lane);
-                u32 te = 0, to = 0;
+                const uint4 *te4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
+                const uint4 *to4 = reinterpret_cast<const uint4 *>(sm.tri_odd + 16 * lane);
+                u32 te[8], to[8];
+                { const uint4 a = te4[0], c = te4[1]; te[0] = a.x; te[1] = a.y; te[2] = a.z; te[3] = a.w; te[4] = c.x; te[5] = c.y; te[6] = c.z; te[7] = c.w; }
+                { const uint4 a = to4[0], c = to4[1]; to[0] = a.x; to[1] = a.y; to[2] = a.z; to[3] = a.w; to[4] = c.x; to[5] = c.y; to[6] = c.z; to[7] = c.w; }
+                // running totals; the part below the lane's filter boundary is the total captured at i + 1 == split.
+                // (the empty asm keeps the 32 frame-invariant compares from being hoisted out of the frame loop, where
+                // ptxas would pack them into a bit mask that costs ~100 instructions per frame to rebuild and unpack)
+                int spe = sp_e, spo = sp_o;
+                asm volatile("" : "+r"(spe), "+r"(spo));
+                u32 s0e = 0, tote = 0, s0o = 0, toto = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint4 we = we4[j], wo = wo4[j];
-                    uint4 pe, po;                                           // running totals BEFORE bin 4j+c
-                    pe.x = te; te += (E[4 * j] * we.x) / 100u;      po.x = to; to += (E[4 * j] * wo.x) / 100u;
-                    pe.y = te; te += (E[4 * j + 1] * we.y) / 100u;  po.y = to; to += (E[4 * j + 1] * wo.y) / 100u;
-                    pe.z = te; te += (E[4 * j + 2] * we.z) / 100u;  po.z = to; to += (E[4 * j + 2] * wo.z) / 100u;
-                    pe.w = te; te += (E[4 * j + 3] * we.w) / 100u;  po.w = to; to += (E[4 * j + 3] * wo.w) / 100u;
-                    re4[j ^ fsw] = pe; ro4[j ^ fsw] = po;
+                for (int i = 0; i < 16; ++i) {
+                    const u32 we = (i & 1) ? (te[i >> 1] >> 16) : (te[i >> 1] & 0xFFFFu);
+                    const u32 wo = (i & 1) ? (to[i >> 1] >> 16) : (to[i >> 1] & 0xFFFFu);
+                    const u32 ve = (E[i] * we) / 100u, vo = (E[i] * wo) / 100u;
+                    tote += ve; toto += vo;
+                    if (i + 1 == spe) s0e = tote;
+                    if (i + 1 == spo) s0o = toto;
                 }
-                if (kFilt == 1) {
-                    // X[l] = sum of the lane totals below lane l; X[32] = grand total (the upper end of filter 23 is bin 512)
-                    u32 ie = te, io = to;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const u32 ue = __shfl_up_sync(0xFFFFFFFFu, ie, o), uo = __shfl_up_sync(0xFFFFFFFFu, io, o);
-                        if (lane >= o) { ie += ue; io += uo; }
-                    }
-                    fb[kFltX + lane] = ie - te;
-                    fb[kFltX + 33 + lane] = io - to;
-                    if (lane == 31) { fb[kFltX + 32] = ie; fb[kFltX + 33 + 32] = io; }
-                } else {                                                    // lane totals as they are: the reader adds the few it spans
-                    fb[kFltX + lane] = te;
-                    fb[kFltX + 33 + lane] = to;
-                }
+                *reinterpret_cast<uint2 *>(&sm.seq[warp][0][2 * lane]) = make_uint2(s0e, tote - s0e);
+                *reinterpret_cast<uint2 *>(&sm.seq[warp][1][2 * lane]) = make_uint2(s0o, toto - s0o);
             }
             __syncwarp();
             // ---- filter totals + log, MFCC.C:165-170 -------------------------------------------
             {
-                u32 acc;
-                if (kFilt == 1) acc = (fb[fx_hi] + fb[fe_hi]) - (fb[fx_lo] + fb[fe_lo]);
-                else {
-                    // S(hi) - S(lo) = e_hi - e_lo + the totals of lanes [lo>>4, hi>>4): at most 6 of them (widest filter 85 bins);
-                    // independent predicated loads instead of a 5-step warp scan (a long dependent chain with 4 warps per scheduler)
-                    acc = fb[fe_hi] - fb[fe_lo];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) if (fx_lo + j < fx_hi) acc += fb[fx_lo + j];
-                }
+                u32 acc = 0;
+                for (int e = flo; e <= fhi; ++e) acc += sm.seq[warp][fpar][e];
                 sm.lg[warp][lane] = (lane < 24) ? log100(acc, sm.log_thr) : 0u;
             }
             __syncwarp();
@@ -417,84 +392,29 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 // C+-D sums of the butterflies onto the ALU pipe as three-input adds (4.86 vs 4.76), two 16-bit
 // stores instead of PRMT + one 32-bit store in block A (4.86 vs 4.80), 20 warps @ 96 regs (5.29 ms vs 5.31), 24 warps @ 80 regs (5.48 ms) -- the half-rate ALU and
 // FMA-heavy pipes, not occupancy, bound the kernel.
-#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG, FILT)                                                               \
+#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG)                                                                  \
     __global__ void __maxnreg__(NREG) mfcc_kernel_##NAME(const u16 *__restrict__ pcm, u32 U, u32 B,              \
                                                          const u32 *__restrict__ seg, u32 seg_stride,            \
                                                          const atap_tag *__restrict__ atap,                       \
                                                          unsigned char *__restrict__ ftr,                         \
                                                          const DevTables *__restrict__ tab,                       \
-                                                         const u32 *__restrict__ row_map, u32 rows_total,        \
-                                                         const u32 *__restrict__ B_dev) {                         \
-        mfcc_body<W, NB, SELF, FILT>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);     \
+                                                         const u32 *__restrict__ row_map, u32 rows_total) {      \
+        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total);                  \
     }
-SR_MFCC_VARIANT(s16, 16, 4, true, 128, 2)
-SR_MFCC_VARIANT(s16scan, 16, 4, true, 128, 1)
-SR_MFCC_VARIANT(w15, 15, 3, false, 128, 2)
-
-// ---- generic (unpruned) FFT + magnitude: the reference's global `fft` (MFCC.C:27-62) -----------
-// One warp per frame, all five passes in shared memory exactly as the asm orders them. Not on the
-// hot path; it exists for the secondary drop-in symbol and as an on-device cross-check of the
-// pruned blocking above with arbitrary (complex, full-length) inputs.
-__global__ void __launch_bounds__(128)
-fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, const s16 *__restrict__ frames, u32 len,
-                   u32 n, u32 *__restrict__ raw_out /*[n][1024] or NULL*/, u32 *__restrict__ mag /*[n][512] or NULL*/,
-                   const DevTables *__restrict__ tab) {
-    __shared__ u32 buf[4][1024];
-    __shared__ u32 src[4][1024];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 fr = blockIdx.x * 4 + warp;
-    if (fr >= n) return;
-    u32 *x = src[warp], *y = buf[warp];
-    for (int i = lane; i < 1024; i += 32) {
-        u32 v;
-        if (in) v = in[(size_t)fr * 1024 + i];
-        else v = (u32)i < len ? (u32)(u16)frames[(size_t)fr * len + i] : 0u;     // MFCC.C:37-45
-        x[i] = v;
-    }
-    __syncwarp();
-    for (int idx = lane; idx < 256; idx += 32) {                                 // .s:226-232
-        const int j = (int)(__brev((u32)idx) >> 24);
-        const u32 A = x[j], C = x[j + 256], Bv = x[j + 512], D = x[j + 768];
-        u32 o[8];
-        cxadda4<0>(lo16s(A), hi16s(A), lo16s(Bv), hi16s(Bv), lo16s(C), hi16s(C), lo16s(D), hi16s(D),
-                   o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) y[4 * idx + m] = pack16(o[2 * m], o[2 * m + 1]);
-    }
-    __syncwarp();
-    int toff = 0;
-    for (int s = 4; s <= 256; s <<= 2) {                                         // .s:254-279
-        for (int t = lane; t < 256; t += 32) {
-            const int q = t % s, base = (t / s) * 4 * s;
-            const int2 k3 = tab->tw[(toff + q) * 3], k2 = tab->tw[(toff + q) * 3 + 1], k1 = tab->tw[(toff + q) * 3 + 2];
-            const u32 p0 = y[base + q], p1 = y[base + q + s], p2 = y[base + q + 2 * s], p3 = y[base + q + 3 * s];
-            u32 Dr, Di, Cr, Ci, Br, Bi, o[8];
-            cxmul(Dr, Di, lo16s(p3), hi16s(p3), (u32)k3.x, (u32)k3.y);
-            cxmul(Cr, Ci, lo16s(p2), hi16s(p2), (u32)k2.x, (u32)k2.y);
-            cxmul(Br, Bi, lo16s(p1), hi16s(p1), (u32)k1.x, (u32)k1.y);
-            cxadda4<14>(lo16s(p0), hi16s(p0), Br, Bi, Cr, Ci, Dr, Di, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
-#pragma unroll
-            for (int m = 0; m < 4; ++m) y[base + q + m * s] = pack16(o[2 * m], o[2 * m + 1]);
-        }
-        __syncwarp();
-        toff += s;
-    }
-    if (raw_out) for (int i = lane; i < 1024; i += 32) raw_out[(size_t)fr * 1024 + i] = y[i];
-    if (mag) for (int i = lane; i < 512; i += 32) mag[(size_t)fr * 512 + i] = mag10(lo16s(y[i]), hi16s(y[i]));
-}
+SR_MFCC_VARIANT(r1s16, 16, 4, true, 128)
 
 // ---- host launchers -----------------------------------------------------------------------------
 template <int W, int NB, bool SELF, typename K>
 static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride,
                                        const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st,
-                                       const u32 *row_map, u32 rows_total, const u32 *B_dev) {
+                                       const u32 *row_map, u32 rows_total) {
     const size_t smem = sizeof(MfccSmem<W, NB>);
     const int threads = (SELF ? W : W + 1) * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
     kern<<<grid, threads, smem, st>>>(pcm, U, B, seg, seg_stride, atap, static_cast<unsigned char *>(ftr), tab, row_map,
-                                      rows_total, B_dev);
+                                      rows_total);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
@@ -506,33 +426,14 @@ static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, con
     return e;
 }
 
-cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
-                        void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total, const u32 *B_dev) {
+}  // namespace r1
+
+cudaError_t launch_mfcc_r1(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
+                           void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total) {
     if (B == 0) return cudaSuccess;
     const DevTables *tab = dev_tables();
     if (!tab) return cudaErrorInitializationError;
-    static int variant = -1;                               // SR_MFCC_WARPS=15 selects the dedicated-producer variant (tuning knob)
-    if (variant < 0) {
-        const char *ev = getenv("SR_MFCC_WARPS");
-        variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
-    }
-    static int filt = -1;                                  // SR_MFCC_FILT: 0 round-1 split capture (A/B baseline), 1 prefix sums + warp scan, 2 prefix sums + reader sum (default)
-    if (filt < 0) { const char *ev = getenv("SR_MFCC_FILT"); filt = ev ? atoi(ev) : 2; }
-    if (filt == 0 && !B_dev) return launch_mfcc_r1(pcm, U, B, seg, seg_stride, atap, ftr, num_sms, st, row_map, rows_total);
-    if (filt == 1)
-        return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16scan, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    if (variant == 15)
-        return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-}
-
-cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
-                               cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    const DevTables *tab = dev_tables();
-    if (!tab) return cudaErrorInitializationError;
-    fft_generic_kernel<<<(n + 3) / 4, 128, 0, st>>>(in_packed, frames, len, n, raw_out, mag, tab);
-    return cudaGetLastError();
+    return r1::launch_mfcc_variant<16, 4, true>(r1::mfcc_kernel_r1s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total);
 }
 
 }  // namespace srk

@@ -320,19 +320,34 @@ static int streams_push_impl(sr_stream_pool *p, const uint16_t *chunk, uint32_t 
     SR_REQUIRE(h, max_len == 0 || chunk != nullptr);
     SR_REQUIRE(h, max_len <= p->L && chunk_stride >= max_len);
     DeviceGuard g(h->device);
+    const u16 *chunk_dev = static_cast<const u16 *>(p->stage.p);
+    u32 chunk_dev_stride = p->stage_stride;
     if (max_len) {
-        // staging rows start 16-byte aligned so the append can use 16-byte copies
-        const u32 sstride = (max_len + 7u) & ~7u;
-        SR_CK(h, ensure(p->stage, (size_t)p->S * sstride * 2 + 64));
-        p->stage_stride = sstride;
-        SR_CK(h, cudaMemcpy2DAsync(p->stage.p, (size_t)sstride * 2, chunk, (size_t)chunk_stride * 2, (size_t)max_len * 2, p->S,
-                                   cudaMemcpyHostToDevice, h->stream));
+        // Pinned (cudaHostAlloc / cudaHostRegister / sr_host_alloc*) chunks are read by the kernel straight from host memory:
+        // one coalesced 16-byte-per-lane read per stream row, no copy-engine descriptor per row (a strided [S][chunk] slice
+        // of a larger capture array is 8192 rows of a few hundred bytes: the 2-D copy alone took ~2 ms). Pageable memory
+        // goes through a device staging buffer.
+        cudaPointerAttributes attr;
+        bool zero_copy = false;
+        if (cudaPointerGetAttributes(&attr, chunk) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            chunk_dev = static_cast<const u16 *>(attr.devicePointer);
+            chunk_dev_stride = chunk_stride;
+            zero_copy = true;
+        } else cudaGetLastError();
+        if (!zero_copy) {
+            const u32 sstride = (max_len + 7u) & ~7u;                    // staging rows start 16-byte aligned
+            SR_CK(h, ensure(p->stage, (size_t)p->S * sstride * 2 + 64));
+            p->stage_stride = sstride;
+            chunk_dev = static_cast<const u16 *>(p->stage.p); chunk_dev_stride = sstride;
+            SR_CK(h, cudaMemcpy2DAsync(p->stage.p, (size_t)sstride * 2, chunk, (size_t)chunk_stride * 2, (size_t)max_len * 2, p->S,
+                                       cudaMemcpyHostToDevice, h->stream));
+        }
         if (lens) SR_CK(h, cudaMemcpyAsync(p->lens.p, p->lens_host, (size_t)p->S * 4, cudaMemcpyHostToDevice, h->stream));
     }
     SR_CK(h, cudaMemsetAsync(p->n_ev.p, 0, 4, h->stream));
     u32 *n_ev = static_cast<u32 *>(p->n_ev.p);
     stream_step_kernel<<<(p->S + kStreamWarps - 1) / kStreamWarps, kStreamWarps * 32, 0, h->stream>>>(
-        static_cast<u16 *>(p->pcm.p), p->L, p->S, static_cast<const u16 *>(p->stage.p), p->stage_stride, max_len ? uniform_len : 0u,
+        static_cast<u16 *>(p->pcm.p), p->L, p->S, chunk_dev, chunk_dev_stride, max_len ? uniform_len : 0u,
         (lens && max_len) ? static_cast<const u32 *>(p->lens.p) : nullptr, p->n_len, static_cast<StreamState *>(p->state.p),
         static_cast<u32 *>(p->info.p), p->info_stride, static_cast<StreamEventDev *>(p->ev.p), static_cast<u32 *>(p->seg_ev.p),
         static_cast<atap_tag *>(p->atap_ev.p), static_cast<u32 *>(p->map_ev.p), n_ev, p->cap);

@@ -644,15 +644,21 @@ def test_streaming_equals_batch(handle, ora, chunk):
     handle.set_bank(bank, T, 4096)
     pool = sr_b200.StreamPool(handle, S, L, 2400)
     events, latest = [], {}
+    pin_ptr = None
+    if chunk == 800:                                   # pinned capture array: chunks are read zero-copy, strided ([S][L] rows)
+        arr, pin_ptr = sr_b200.host_alloc_dev(0, S * L * 2)
+        arr.view(np.uint16).reshape(S, L)[:] = pcm
     for n0 in range(0, L, chunk):
         c = np.ascontiguousarray(pcm[:, n0:n0 + chunk])
-        evs = pool.push(c)
+        evs = pool.push(pin_ptr + 2 * n0, c.shape[1], L) if pin_ptr else pool.push(c)
         for e in evs:
             # the segment closes with the chunk that delivers sample end+879 (last sample of the closing frame)
             assert n0 <= e["end"] + 879 < n0 + c.shape[1]
         events += evs
     seg, atap = pool.segments()
     pool.close()
+    if pin_ptr:
+        sr_b200.host_free(pin_ptr)
     batch_atap = handle.noise_atap(pcm, 2400)
     assert atap.tobytes() == batch_atap.tobytes()
     batch_seg = handle.vad(pcm, batch_atap)

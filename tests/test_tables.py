@@ -131,6 +131,7 @@ def test_prefix_sum_filter_model_equals_direct_sums():
             E[:] = 0xFFFFFFFF
         fb = np.zeros(1152, np.uint64)
         X = np.zeros((2, 33), np.uint64)
+        TOT = [None, None]
         for par in range(2):
             v = ((E * tri[par]) & M) // np.uint64(100)
             tot = np.zeros(32, np.uint64)
@@ -140,12 +141,18 @@ def test_prefix_sum_filter_model_equals_direct_sums():
                     fb[par * 512 + word(l, i)] = run
                     run = (run + v[16 * l + i]) & M
                 tot[l] = run
+            TOT[par] = tot
             inc = np.cumsum(tot) & M
             X[par, :32] = (inc - tot) & M
             X[par, 32] = inc[31]
         for h in range(24):
             par = h & 1
             got = ((X[par, xhi[h]] + fb[ehi[h]]) - (X[par, xlo[h]] + fb[elo[h]])) & M
+            got2 = (fb[ehi[h]] - fb[elo[h]]) & M                       # the form without the scan: e_hi - e_lo + spanned lane totals
+            assert int(xhi[h]) - int(xlo[h]) <= 6
+            for l in range(int(xlo[h]), int(xhi[h])):
+                got2 = (got2 + TOT[par][l]) & M
+            assert got2 == got
             a, b = (0, cen[1]) if h == 0 else ((cen[22], 512) if h == 23 else (cen[h - 1], cen[h + 1]))
             want = np.uint64(0)
             for k in range(a, b):
