@@ -765,15 +765,16 @@ def run_stream_shard(args, torch, dist, sr_b200, h, dev, stream, rank, world, lo
             pool.reset()
             if world > 1:
                 dist.barrier()
-            lat, n_events = [], 0
+            lat, n_events, per_push = [], 0, []
             t_start = time.perf_counter()
             for n0 in range(0, Ls, chunk):
                 t0 = time.perf_counter()
-                evs = pool.push(ptr + 2 * n0, chunk, Ls)
+                ne = pool.push_raw(ptr + 2 * n0, chunk, Ls)   # returns when the events are in host memory
                 dt = time.perf_counter() - t0
-                if evs:
-                    lat += [dt] * len(evs)
-                    n_events += len(evs)
+                if ne:
+                    lat += [dt] * ne
+                    n_events += ne
+                    per_push.append((ne, dt * 1e3))
             t_all = time.perf_counter() - t_start
         if world > 1:
             gathered = [None] * world
@@ -785,6 +786,7 @@ def run_stream_shard(args, torch, dist, sr_b200, h, dev, stream, rank, world, lo
         out["chunk_%d" % chunk] = {"chunk_ms": chunk / 8.0, "pushes": Ls // chunk, "events": n_events,
                                    "latency_ms_p50": float(np.percentile(la, 50)), "latency_ms_p99": float(np.percentile(la, 99)),
                                    "latency_ms_max": float(la.max()), "wall_s": t_all,
+                                   "largest_pushes_events_ms": [[int(a), round(b, 3)] for a, b in sorted(per_push, reverse=True)[:4]],
                                    "realtime_factor": (S_all * Ls / 8000.0) / t_all, "utterances_per_s": n_events / t_all}
     seg, _ = pool.segments()
     pool.close()

@@ -557,7 +557,10 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         if (!h->pool) {
             // packers = this rank's CPU share minus room for the sender, the CUDA runtime's threads and the caller's own work
             static const int env_nt = [] { const char *e = getenv("SR_PACK_THREADS"); return e && *e ? atoi(e) : 0; }();
+            // (measured on a 2 x 32-core host, 16-CPU quota: 8..12 packers all land at ~16.3 ms per 1.05 GB step; more only add
+            // memory traffic next to the DMA reads, which slows the link: 54 -> 47 GB/s at 14 packers)
             int nt = env_nt > 0 ? env_nt : rank_cpu_share() - 3;
+            if (env_nt <= 0 && nt > 10) nt = 10;
             nt = nt > 16 ? 16 : nt;
             if (nt >= 2) h->pool = new (std::nothrow) PackPool(nt);
         }

@@ -447,6 +447,14 @@ class StreamPool:
         self._ck(f(self._p, ptr, chunk_len, stride, self._ev, 3 * self.S if max_events is None else max_events, C.byref(n)))
         return self._events(n.value)
 
+    def push_raw(self, ptr, chunk_len, stride, max_events=None):
+        """lock-step push from a raw host pointer; returns only the NUMBER of events (they stay in self._ev): what a
+        latency measurement should time -- no Python object is built per event"""
+        n = C.c_uint32(0)
+        f = lib().sr_stream_group_push if self.group else lib().sr_streams_push
+        self._ck(f(self._p, C.c_void_p(int(ptr)), chunk_len, stride, self._ev, 3 * self.S if max_events is None else max_events, C.byref(n)))
+        return n.value
+
     def push_ragged(self, chunk, lens, stride=None, max_events=None):
         """chunk: numpy [S, >= max(lens)] u16 (or raw pointer + stride); lens: [S] samples for each stream"""
         lens = np.ascontiguousarray(lens, np.uint32)

@@ -13,11 +13,11 @@ import torch  # noqa: E402
 
 dev = rank % max(1, torch.cuda.device_count())
 sr_b200.lib().sr_bind_thread_to_device(dev)
-B, U, T = 4096 * 5, 8000, 6                       # 5 chunks of 32 MB: the packed path engages (>= 4 chunks)
+B, U, T = 2048 * 5, 8000, 6                       # 5 chunks of 32 MB: the packed path engages (>= 4 chunks)
 arr, p = sr_b200.host_alloc_dev(dev, B * U * 2)
 pcm = arr.view(np.uint16).reshape(B, U)
 pcm[:] = sr_b200.synth_pcm_host(B, U, 0x5EED0000 + rank * B)
-pcm[4096 * 2 + 5, 100] = 60000                    # one chunk holds a sample >= 4096: it must travel plain
+pcm[2048 * 2 + 5, 100] = 60000                    # one chunk holds a sample >= 4096: it must travel plain
 h = sr_b200.Handle(dev)
 bank, _ = h.enrol(sr_b200.synth_pcm_host(T, U, 0x7E3A0000), 2400)
 h.set_bank(bank, T, 4096)
