@@ -164,7 +164,12 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     // ---- one-time: tables to shared memory, barriers ------------------------------------------
     for (int i = threadIdx.x; i < 340 * 3; i += blockDim.x) sm.tw[i] = tab->tw[i];
     for (int i = threadIdx.x; i < 2220; i += blockDim.x) sm.log_thr[i] = tab->log_thr[i];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { sm.tri_even[i] = tab->tri_even[i]; sm.tri_odd[i] = tab->tri_odd[i]; }
+    // filter weights in the same bank-swizzled row layout as the running totals (flt_word): a lane reads its 16 weights with
+    // four 16-byte loads, and eight neighbouring lanes hit 32 distinct banks (plain 16-word rows would conflict 4-way)
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        sm.tri_even[flt_word(i >> 4, i & 15)] = tab->tri_even[i];
+        sm.tri_odd[flt_word(i >> 4, i & 15)] = tab->tri_odd[i];
+    }
     for (int i = threadIdx.x; i < kConsumerWarps; i += blockDim.x) sm.fftbuf[i][kFltZero] = 0u;   // S(512)'s in-lane part
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNBuf; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
@@ -352,7 +357,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                 u32 te = 0, to = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint4 we = we4[j], wo = wo4[j];
+                    const uint4 we = we4[j ^ fsw], wo = wo4[j ^ fsw];
                     uint4 pe, po;                                           // running totals BEFORE bin 4j+c
                     pe.x = te; te += (E[4 * j] * we.x) / 100u;      po.x = to; to += (E[4 * j] * wo.x) / 100u;
                     pe.y = te; te += (E[4 * j + 1] * we.y) / 100u;  po.y = to; to += (E[4 * j + 1] * wo.y) / 100u;
