@@ -127,11 +127,12 @@ __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int g = (8 * c + 2 * j) >> 5;
-                u32 mx, mn;
-                asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(w[j]), "r"(mid2));
+                u32 mn;
                 asm("min.u16x2 %0, %1, %2;" : "=r"(mn) : "r"(w[j]), "r"(mid2));
-                bsx = __dp2a_lo(mx, 0x0101u, bsx);                          // VAD.C:126-129: sum |x-mid| = sum max - sum min; two
-                bsn = __dp2a_lo(mn, 0x0101u, bsn);                          // IDP.2A (FMA pipe) instead of a subtract on the busy ALU pipe
+                // VAD.C:126-129: |x-mid| = max - min = x + mid - 2 min(x, mid): one packed min (ALU pipe, the busy one) and two
+                // IDP.2A sums (FMA pipe) per sample pair; the block total is assembled after the loop
+                bsx = __dp2a_lo(w[j], 0x0101u, bsx);
+                bsn = __dp2a_lo(mn, 0x0101u, bsn);
                 asm("{\n .reg .u32 t, l;\n shl.b32 l, %2, 16;\n"
                     " add.cc.u32 t, l, %3;\n madc.lo.u32 %0, %0, 2, 0;\n"  // VAD.C:134-141 / 143-156, low sample
                     " add.cc.u32 t, l, %4;\n madc.lo.u32 %1, %1, 2, 0;\n"
@@ -141,7 +142,7 @@ __device__ __forceinline__ void block_scan(const VadWarpView &v, u32 i0, u32 mid
                     : "r"(w[j]), "r"(na), "r"(nb));
             }
         }
-        bs = bsx - bsn;
+        bs = bsx + 80u * mid - 2u * bsn;
         H[0] = __brev(gA[0]); H[1] = __brev(gA[1]); H[2] = __brev(gA[2]) >> 16;
         L[0] = ~__brev(gB[0]); L[1] = ~__brev(gB[1]); L[2] = ~(__brev(gB[2]) >> 16) & 0xFFFFu;
         if (a_thl == 0) { H[0] = 0xFFFFFFFFu; H[1] = 0xFFFFFFFFu; H[2] = 0xFFFFu; }   // s >= 0 always
