@@ -149,7 +149,7 @@ __device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> 
 // kSelf = false: warp kConsumerWarps is a dedicated producer. kSelf = true: every warp is a consumer and the staging
 // of utterance it+kAhead is a side job of warp it % kConsumerWarps at the top of iteration it, so all four
 // schedulers of the SM carry the same number of working warps.
-template <int kConsumerWarps, int kNBuf, bool kSelf, int kFilt, bool kPre>
+template <int kConsumerWarps, int kNBuf, bool kSelf, int kFilt>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
                                           unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
@@ -247,11 +247,10 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                 wq[i] = w >> 2;                                           // BUTFLY4ZERO_OPT with B=C=D=0
             }
         };
-        bool wq_ready = false;                                            // wq already holds the next frame (computed in the previous iteration's filter stage)
         for (int f = (int)((warp - (int)(gidx % kConsumerWarps) + kConsumerWarps) % kConsumerWarps); f < F;
              f += kConsumerWarps) {
             const u16 *xf = x + 80 * f;                                  // xf[i] = vc_dat[i-1]
-            if (!kPre || !wq_ready) preemph(xf);
+            preemph(xf);
             __syncwarp();
 
             // ---- block A: stages 1+2 -----------------------------------------------------------
@@ -352,12 +351,6 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const uint4 v = e4[j]; E[4 * j] = v.x; E[4 * j + 1] = v.y; E[4 * j + 2] = v.z; E[4 * j + 3] = v.w; }
                 __syncwarp();                                               // every lane holds its energies: fb is scratch now
-                // software pipelining by hand: the next frame of this warp (same utterance) is windowed here, where wq is
-                // free (block A consumed it) and its shared-memory loads overlap the filter products and vice versa
-                if (kPre) {
-                    wq_ready = f + kConsumerWarps < F;
-                    if (wq_ready) preemph(xf + 80 * kConsumerWarps);
-                }
                 const uint4 *we4 = reinterpret_cast<const uint4 *>(sm.tri_even + 16 * lane);
                 const uint4 *wo4 = reinterpret_cast<const uint4 *>(sm.tri_odd + 16 * lane);
                 uint4 *re4 = reinterpret_cast<uint4 *>(fb + 16 * lane);                    // this lane's row, group g at slot g ^ fsw
@@ -430,7 +423,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 // C+-D sums of the butterflies onto the ALU pipe as three-input adds (4.86 vs 4.76), two 16-bit
 // stores instead of PRMT + one 32-bit store in block A (4.86 vs 4.80), 20 warps @ 96 regs (5.29 ms vs 5.31), 24 warps @ 80 regs (5.48 ms) -- the half-rate ALU and
 // FMA-heavy pipes, not occupancy, bound the kernel.
-#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG, FILT, PRE)                                                               \
+#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG, FILT)                                                               \
     __global__ void __maxnreg__(NREG) mfcc_kernel_##NAME(const u16 *__restrict__ pcm, u32 U, u32 B,              \
                                                          const u32 *__restrict__ seg, u32 seg_stride,            \
                                                          const atap_tag *__restrict__ atap,                       \
@@ -438,17 +431,13 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                                                          const DevTables *__restrict__ tab,                       \
                                                          const u32 *__restrict__ row_map, u32 rows_total,        \
                                                          const u32 *__restrict__ B_dev) {                         \
-        mfcc_body<W, NB, SELF, FILT, PRE>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);\
+        mfcc_body<W, NB, SELF, FILT>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);     \
     }
-SR_MFCC_VARIANT(s16, 16, 4, true, 128, 2, false)
-SR_MFCC_VARIANT(s16pre, 16, 4, true, 128, 2, true)
-SR_MFCC_VARIANT(s16scan, 16, 4, true, 128, 1, false)
-SR_MFCC_VARIANT(w15, 15, 3, false, 128, 2, false)
-SR_MFCC_VARIANT(s20, 20, 4, true, 102, 2, false)
-SR_MFCC_VARIANT(s20pre, 20, 4, true, 102, 2, true)
-//      // occupancy experiments (SR_MFCC_WARPS=20 / 24): more warps to hide the
-SR_MFCC_VARIANT(s24, 24, 3, true, 85, 2, false)
-//       // shared-memory latency that ncu shows as the top stall after the pipes
+SR_MFCC_VARIANT(s16, 16, 4, true, 128, 2)
+SR_MFCC_VARIANT(s16scan, 16, 4, true, 128, 1)
+SR_MFCC_VARIANT(w15, 15, 3, false, 128, 2)
+SR_MFCC_VARIANT(s20, 20, 4, true, 96, 2)        // occupancy experiments (SR_MFCC_WARPS=20 / 24): more warps to hide the
+SR_MFCC_VARIANT(s24, 24, 3, true, 80, 2)         // shared-memory latency that ncu shows as the top stall after the pipes
 
 // ---- generic (unpruned) FFT + magnitude: the reference's global `fft` (MFCC.C:27-62) -----------
 // One warp per frame, all five passes in shared memory exactly as the asm orders them. Not on the
@@ -540,12 +529,6 @@ cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_st
     if (filt == 0 && !B_dev) return launch_mfcc_r1(pcm, U, B, seg, seg_stride, atap, ftr, num_sms, st, row_map, rows_total);
     if (filt == 1)
         return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16scan, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    static int pre = -1;                                   // SR_MFCC_PRE=1: window the next frame during the filter stage
-    if (pre < 0) { const char *ev = getenv("SR_MFCC_PRE"); pre = ev ? atoi(ev) : 0; }
-    if (variant == 20 && pre)
-        return launch_mfcc_variant<20, 4, true>(mfcc_kernel_s20pre, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    if (variant == 16 && pre && filt == 2)
-        return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16pre, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
     if (variant == 20)
         return launch_mfcc_variant<20, 4, true>(mfcc_kernel_s20, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
     if (variant == 24)
