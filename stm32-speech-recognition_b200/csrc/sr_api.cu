@@ -323,6 +323,15 @@ int sr_dtw_batch_dev(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t fla
 
 int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len,
                            const sr_recog_out *o) {
+    return recognise_dev_impl(h, pcm, U, B, n_len, o, false);
+}
+
+}  // extern "C"
+
+// wait_comm: order the template scan (the first kernel that rewrites score / best) after the handle's pending collective,
+// so that an all-gather of the previous batch overlaps this batch's VAD and MFCC (sr_comm.cu)
+int recognise_dev_impl(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, const sr_recog_out *o,
+                       bool wait_comm) {
     SR_REQUIRE(h, h && o && (B == 0 || pcm));
     SR_REQUIRE(h, U <= 65535u && n_len <= U);
     if (B == 0) return 0;
@@ -345,9 +354,12 @@ int sr_recognise_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32
     { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, pcm, U, B, seg, 6, atap, ftr)); }
     { TimedLaunch tl(h, TAG_STATUS); SR_CK(h, launch_status(seg, ftr, B, status, h->stream)); }
     h->launches += 3;
+    if (wait_comm) { const int rc = sr_comm_wait(h); if (rc) return rc; }
     // main.c:276-294 template scan, argmin, command index
     return dtw_dev_impl(h, ftr, B, SR_DTW_CHECK_SIGN, 0, o->score, o->best_idx, o->best_dis, o->cmd, status);
 }
+
+extern "C" {
 
 // ---- host-buffer entry points ---------------------------------------------------------------------
 
@@ -438,14 +450,33 @@ static int rank_cpu_share() {
     return usable_cpus() / local_world;
 }
 
-static bool transport_enabled(const sr_handle *h) {
+// 1 = forced on, 0 = forced off, -1 = automatic (decided per call by transport_auto_pick)
+static int transport_mode(const sr_handle *h) {
     int mode = h->transport_mode;
     if (mode < 0) {
         static const int env_mode = [] { const char *e = getenv("SR_PACK12"); return e && *e ? atoi(e) : -1; }();
         mode = env_mode;
     }
-    if (mode < 0) mode = SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6 ? 1 : 0;
-    return mode > 0;
+    if (mode < 0 && !(SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6)) mode = 0;
+    return mode;
+}
+
+// Automatic mode measures instead of guessing. Whether packing pays depends on what else loads the host's memory system:
+// one or two ranks per socket gain ~16 % (16.3 vs 19.4 ms per 1.05 GB), but with four ranks per socket the DMA reads
+// alone take ~216 GB/s of that socket's DRAM bandwidth and the packers' extra traffic makes the call SLOWER (25.8 vs
+// 19.5 ms, measured at 4 and 8 GPUs). So: the first qualifying call goes plain, the second packed, then the faster of
+// the two (ns per byte, exponentially averaged) is used, with the other re-probed every 32nd call.
+static bool transport_auto_pick(sr_handle *h) {
+    const uint64_t n = h->auto_calls++;
+    if (h->auto_ns_per_byte[0] <= 0.0) return false;
+    if (h->auto_ns_per_byte[1] <= 0.0) return true;
+    const bool packed_better = h->auto_ns_per_byte[1] < h->auto_ns_per_byte[0];
+    if (n % 32 == 31) return !packed_better;                       // probe the loser now and then: conditions change
+    return packed_better;
+}
+static void transport_auto_record(sr_handle *h, bool packed, double ns_per_byte) {
+    double &v = h->auto_ns_per_byte[packed ? 1 : 0];
+    v = v <= 0.0 ? ns_per_byte : 0.75 * v + 0.25 * ns_per_byte;
 }
 
 int sr_set_transport(sr_handle *h, int mode) {
@@ -550,7 +581,10 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     };
     h->chunk_seq = 0; h->last_packed = 0; h->last_plain = 0; h->last_h2d = 0;
 
-    bool packed_transport = nchunks >= 4 && transport_enabled(h);
+    const int tmode = nchunks >= 4 ? transport_mode(h) : 0;
+    const bool tauto = tmode < 0;
+    bool packed_transport = tmode > 0 || (tauto && transport_auto_pick(h));
+    const auto t_call0 = std::chrono::steady_clock::now();
     if (packed_transport) {                              // workers, pinned staging slots, device staging
         const size_t pk = ((((size_t)chunk * U + 1) / 2 * 3 + 64 + 255) / 256) * 256;
         ScopedNodeAffinity node_scope(h->numa_node);      // workers inherit it; staging pages are allocated from this node
@@ -663,6 +697,9 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     if (o->cmd) D2H(h, o->cmd, d.cmd, (size_t)B * 4);
     if (o->status) D2H(h, o->status, d.status, (size_t)B);
     SR_CK(h, cudaStreamSynchronize(h->stream));
+    if (tauto)
+        transport_auto_record(h, packed_transport && h->last_packed > 0,
+                              std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_call0).count() / ((double)B * U * 2.0));
     return 0;
 }
 

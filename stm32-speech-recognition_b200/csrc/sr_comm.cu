@@ -25,6 +25,8 @@ struct NcclApi {
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     int (*GetVersion)(int *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     std::string why;
 };
 
@@ -47,6 +49,8 @@ NcclApi *nccl_api() {
         api.AllGather = reinterpret_cast<int (*)(const void *, void *, size_t, int, ncclComm_p, cudaStream_t)>(sym("ncclAllGather"));
         api.GetErrorString = reinterpret_cast<const char *(*)(int)>(sym("ncclGetErrorString"));
         api.GetVersion = reinterpret_cast<int (*)(int *)>(sym("ncclGetVersion"));
+        api.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
     });
     return &api;
 }
@@ -115,7 +119,10 @@ int sr_comm_create(sr_handle *h, int rank, int world, const void *id128) {
     SR_REQUIRE(h, c != nullptr);
     c->rank = rank; c->world = world;
     h->comm = c;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    // highest priority: when a persistent kernel's CTAs drain, the collective's few CTAs are placed before the next kernel's
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { sr_comm_destroy(h); return fail(h, "sr_comm_create: stream/event", e); }
@@ -129,20 +136,31 @@ int sr_comm_create(sr_handle *h, int rank, int world, const void *id128) {
 int sr_comm_rank(const sr_handle *h) { return h && h->comm ? h->comm->rank : 0; }
 int sr_comm_world(const sr_handle *h) { return h && h->comm ? h->comm->world : 1; }
 
-// All-gather of equal blocks, device pointers: recv[r*bytes .. ) = rank r's send block. Ordered after everything
-// issued so far on the handle's stream; runs on the communicator's stream (overlaps what the handle does next).
-int sr_allgather_dev(sr_handle *h, const void *send, void *recv, size_t bytes_per_rank) {
-    SR_REQUIRE(h, h && h->comm && (bytes_per_rank == 0 || (send && recv)));
-    if (bytes_per_rank == 0) return 0;
-    DeviceGuard g(h->device);
+// up to two all-gathers of equal blocks as ONE NCCL group (one kernel): recv[r*bytes .. ) = rank r's send block. Ordered
+// after everything issued so far on the handle's stream; runs on the communicator's stream.
+static int allgather2(sr_handle *h, const void *send0, void *recv0, size_t bytes0, const void *send1, void *recv1, size_t bytes1) {
     sr_comm *c = h->comm;
+    NcclApi *a = nccl_api();
     SR_CK(h, cudaEventRecord(c->ev_ready, h->stream));
     SR_CK(h, cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
-    const int rc = nccl_api()->AllGather(send, recv, bytes_per_rank, kNcclUint8, c->comm, c->stream);
+    const bool group = bytes0 && bytes1 && a->GroupStart && a->GroupEnd;
+    int rc = 0;
+    if (group) rc = a->GroupStart();
+    if (!rc && bytes0) rc = a->AllGather(send0, recv0, bytes0, kNcclUint8, c->comm, c->stream);
+    if (!rc && bytes1) rc = a->AllGather(send1, recv1, bytes1, kNcclUint8, c->comm, c->stream);
+    if (group) { const int rc2 = a->GroupEnd(); if (!rc) rc = rc2; }
     if (rc) return nccl_fail(h, "ncclAllGather", rc);
     SR_CK(h, cudaEventRecord(c->ev_done, c->stream));
     c->pending = true;
     return 0;
+}
+
+// All-gather of equal blocks, device pointers (overlaps what the handle's stream does next; see sr_comm_wait)
+int sr_allgather_dev(sr_handle *h, const void *send, void *recv, size_t bytes_per_rank) {
+    SR_REQUIRE(h, h && h->comm && (bytes_per_rank == 0 || (send && recv)));
+    if (bytes_per_rank == 0) return 0;
+    DeviceGuard g(h->device);
+    return allgather2(h, send, recv, bytes_per_rank, nullptr, nullptr, 0);
 }
 
 // make the handle's stream wait for the collectives issued so far (then sr_sync / stream order covers them)
@@ -164,25 +182,18 @@ int sr_recognise_batch_dev_allgather(sr_handle *h, const uint16_t *pcm, uint32_t
     SR_REQUIRE(h, h && h->comm && out_dev);
     SR_REQUIRE(h, !gathered_score || out_dev->score);
     DeviceGuard g(h->device);
-    // the previous gather may still be reading score / best: the kernels that rewrite them wait for it
-    int rc = sr_comm_wait(h);
-    if (rc) return rc;
     sr_recog_out o = *out_dev;
     if (gathered_best && !o.best_idx) {                              // force the argmin so that h->best holds the keys
         SR_CK(h, ensure(h->bidx, (size_t)B * 4));
         o.best_idx = static_cast<u32 *>(h->bidx.p);
     }
-    rc = sr_recognise_batch_dev(h, pcm, U, B, n_len, &o);
+    // The previous batch's gather may still be reading score / best. Only the template scan rewrites them, so only it waits
+    // (inside recognise_dev_impl): this batch's VAD and MFCC overlap the previous gather.
+    int rc = recognise_dev_impl(h, pcm, U, B, n_len, &o, true);
     if (rc) return rc;
-    if (gathered_score) {
-        rc = sr_allgather_dev(h, o.score, gathered_score, (size_t)B * h->n_slot * 4);
-        if (rc) return rc;
-    }
-    if (gathered_best) {
-        rc = sr_allgather_dev(h, h->best.p, gathered_best, (size_t)B * 8);
-        if (rc) return rc;
-    }
-    return 0;
+    if (!gathered_score && !gathered_best) return 0;
+    return allgather2(h, gathered_score ? o.score : nullptr, gathered_score, gathered_score ? (size_t)B * h->n_slot * 4 : 0,
+                      gathered_best ? h->best.p : nullptr, gathered_best, gathered_best ? (size_t)B * 8 : 0);
 }
 
 }  // extern "C"

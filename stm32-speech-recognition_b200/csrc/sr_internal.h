@@ -72,6 +72,8 @@ struct sr_handle {
     size_t ev_used = 0;
     // packed PCM transport (sr_recognise_batch): worker pool, pinned staging slots, device staging
     int transport_mode = -1;                            // 0 off, 1 on, -1 automatic
+    uint64_t auto_calls = 0;                            // automatic mode: calls seen, measured ns per PCM byte [plain, packed]
+    double auto_ns_per_byte[2] = {0.0, 0.0};
     PackPool *pool = nullptr;
     static constexpr int kStage = 4;
     void *stage[kStage] = {nullptr, nullptr, nullptr, nullptr};
@@ -144,6 +146,9 @@ inline cudaError_t launch_dtw_h(sr_handle *h, const void *in_ftr, u32 B, u32 fla
     }
     return launch_dtw(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream, B_dev);
 }
+
+int recognise_dev_impl(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, const sr_recog_out *o,
+                       bool wait_comm);             // sr_api.cu
 
 // records a (start,end) event pair around one kernel launch when timing is enabled
 struct TimedLaunch {

@@ -36,9 +36,6 @@
 
 namespace srk {
 
-cudaError_t launch_mfcc_r1(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
-                           void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total);   // sr_mfcc_r1.cu
-
 constexpr int kPcmBufBytes = 19264;          // (118*80+160+1)*2 = 19202 B + 16 B alignment slack, /64
 constexpr int kFftWords = kFftWordsTotal;    // FFT data: 1024 + 4 words per 64; filter-stage scratch behind it (sr_common.cuh)
 
@@ -149,7 +146,7 @@ __device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> 
 // kSelf = false: warp kConsumerWarps is a dedicated producer. kSelf = true: every warp is a consumer and the staging
 // of utterance it+kAhead is a side job of warp it % kConsumerWarps at the top of iteration it, so all four
 // schedulers of the SM carry the same number of working warps.
-template <int kConsumerWarps, int kNBuf, bool kSelf, int kFilt>
+template <int kConsumerWarps, int kNBuf, bool kSelf>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
                                           unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
@@ -366,34 +363,19 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                     pe.w = te; te += (E[4 * j + 3] * we.w) / 100u;  po.w = to; to += (E[4 * j + 3] * wo.w) / 100u;
                     re4[j ^ fsw] = pe; ro4[j ^ fsw] = po;
                 }
-                if (kFilt == 1) {
-                    // X[l] = sum of the lane totals below lane l; X[32] = grand total (the upper end of filter 23 is bin 512)
-                    u32 ie = te, io = to;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const u32 ue = __shfl_up_sync(0xFFFFFFFFu, ie, o), uo = __shfl_up_sync(0xFFFFFFFFu, io, o);
-                        if (lane >= o) { ie += ue; io += uo; }
-                    }
-                    fb[kFltX + lane] = ie - te;
-                    fb[kFltX + 33 + lane] = io - to;
-                    if (lane == 31) { fb[kFltX + 32] = ie; fb[kFltX + 33 + 32] = io; }
-                } else {                                                    // lane totals as they are: the reader adds the few it spans
-                    fb[kFltX + lane] = te;
-                    fb[kFltX + 33 + lane] = to;
-                }
+                // lane totals as they are: the reader adds the few it spans (a 5-step warp scan of them -- ten dependent
+                // shuffles per frame with four warps per scheduler -- measured 5 % slower)
+                fb[kFltX + lane] = te;
+                fb[kFltX + 33 + lane] = to;
             }
             __syncwarp();
             // ---- filter totals + log, MFCC.C:165-170 -------------------------------------------
             {
-                u32 acc;
-                if (kFilt == 1) acc = (fb[fx_hi] + fb[fe_hi]) - (fb[fx_lo] + fb[fe_lo]);
-                else {
-                    // S(hi) - S(lo) = e_hi - e_lo + the totals of lanes [lo>>4, hi>>4): at most 6 of them (widest filter 85 bins);
-                    // independent predicated loads instead of a 5-step warp scan (a long dependent chain with 4 warps per scheduler)
-                    acc = fb[fe_hi] - fb[fe_lo];
+                // S(hi) - S(lo) = e_hi - e_lo + the totals of lanes [lo>>4, hi>>4): at most 6 of them (widest filter 85 bins),
+                // independent predicated loads
+                u32 acc = fb[fe_hi] - fb[fe_lo];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) if (fx_lo + j < fx_hi) acc += fb[fx_lo + j];
-                }
+                for (int j = 0; j < 6; ++j) if (fx_lo + j < fx_hi) acc += fb[fx_lo + j];
                 sm.lg[warp][lane] = (lane < 24) ? log100(acc, sm.log_thr) : 0u;
             }
             __syncwarp();
@@ -423,7 +405,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 // C+-D sums of the butterflies onto the ALU pipe as three-input adds (4.86 vs 4.76), two 16-bit
 // stores instead of PRMT + one 32-bit store in block A (4.86 vs 4.80), 20 warps @ 96 regs (5.29 ms vs 5.31), 24 warps @ 80 regs (5.48 ms) -- the half-rate ALU and
 // FMA-heavy pipes, not occupancy, bound the kernel.
-#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG, FILT)                                                               \
+#define SR_MFCC_VARIANT(NAME, W, NB, SELF, NREG)                                                                     \
     __global__ void __maxnreg__(NREG) mfcc_kernel_##NAME(const u16 *__restrict__ pcm, u32 U, u32 B,              \
                                                          const u32 *__restrict__ seg, u32 seg_stride,            \
                                                          const atap_tag *__restrict__ atap,                       \
@@ -431,13 +413,10 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                                                          const DevTables *__restrict__ tab,                       \
                                                          const u32 *__restrict__ row_map, u32 rows_total,        \
                                                          const u32 *__restrict__ B_dev) {                         \
-        mfcc_body<W, NB, SELF, FILT>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);     \
+        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);           \
     }
-SR_MFCC_VARIANT(s16, 16, 4, true, 128, 2)
-SR_MFCC_VARIANT(s16scan, 16, 4, true, 128, 1)
-SR_MFCC_VARIANT(w15, 15, 3, false, 128, 2)
-SR_MFCC_VARIANT(s20, 20, 4, true, 96, 2)        // occupancy experiments (SR_MFCC_WARPS=20 / 24): more warps to hide the
-SR_MFCC_VARIANT(s24, 24, 3, true, 80, 2)         // shared-memory latency that ncu shows as the top stall after the pipes
+SR_MFCC_VARIANT(s16, 16, 4, true, 128)
+SR_MFCC_VARIANT(w15, 15, 3, false, 128)
 
 // ---- generic (unpruned) FFT + magnitude: the reference's global `fft` (MFCC.C:27-62) -----------
 // One warp per frame, all five passes in shared memory exactly as the asm orders them. Not on the
@@ -524,15 +503,6 @@ cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_st
         const char *ev = getenv("SR_MFCC_WARPS");
         variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
     }
-    static int filt = -1;                                  // SR_MFCC_FILT: 0 round-1 split capture (A/B baseline), 1 prefix sums + warp scan, 2 prefix sums + reader sum (default)
-    if (filt < 0) { const char *ev = getenv("SR_MFCC_FILT"); filt = ev ? atoi(ev) : 2; }
-    if (filt == 0 && !B_dev) return launch_mfcc_r1(pcm, U, B, seg, seg_stride, atap, ftr, num_sms, st, row_map, rows_total);
-    if (filt == 1)
-        return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16scan, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    if (variant == 20)
-        return launch_mfcc_variant<20, 4, true>(mfcc_kernel_s20, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    if (variant == 24)
-        return launch_mfcc_variant<24, 3, true>(mfcc_kernel_s24, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
     if (variant == 15)
         return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
     return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);

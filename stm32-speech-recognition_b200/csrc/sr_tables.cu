@@ -26,20 +26,6 @@ static void build_tables(DevTables &t) {
     for (int j = 1; j <= 12; ++j) bnd[0][j] = cen[2 * j - 1];
     for (int j = 0; j < 12; ++j) bnd[1][j] = cen[2 * j];
     bnd[1][12] = 512;
-    for (int par = 0; par < 2; ++par) {                      // round-1 partition (sr_mfcc_r1.cu)
-        u8 *split = par ? t.split_odd : t.split_even;
-        for (int L = 0; L < 32; ++L) {
-            split[L] = 16;
-            for (int j = 0; j <= 12; ++j)
-                if (bnd[par][j] >= 16 * L && bnd[par][j] <= 16 * L + 16) split[L] = (u8)(bnd[par][j] - 16 * L);
-        }
-        for (int j = 0; j < 12; ++j) {
-            const int h = 2 * j + par, lo = bnd[par][j], hi = bnd[par][j + 1];
-            const int Ll = lo >> 4, Lh = (hi - 1) >> 4;
-            t.seq_lo[h] = (u8)(2 * Ll + ((lo - 16 * Ll) >= split[Ll] ? 1 : 0));
-            t.seq_hi[h] = (u8)(2 * Lh + ((hi - 1 - 16 * Lh) >= split[Lh] ? 1 : 0));
-        }
-    }
     for (int par = 0; par < 2; ++par)
         for (int j = 0; j < 12; ++j) {
             const int h = 2 * j + par, lo = bnd[par][j], hi = bnd[par][j + 1];
