@@ -340,8 +340,8 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
 
             // ---- triangular filters, MFCC.C:136-162: lane owns bins [16*lane, 16*lane+16) ------
             // acc[h] = sum over the filter's bins of (E[k]*tri[k])/100, u32 wrap. Per parity the per-bin terms become
-            // prefix sums: a lane keeps the running totals of its 16 bins (written to the warp's scratch), the lane
-            // totals are scanned over the warp, and a filter is a difference of two prefix values -- exact mod 2^32.
+            // prefix sums: a lane keeps the running totals of its 16 bins (written to the warp's scratch) and its total;
+            // a filter is a difference of two prefix values (running totals + the lane totals in between) -- exact mod 2^32.
             {
                 u32 E[16];
                 const uint4 *e4 = reinterpret_cast<const uint4 *>(fb + 16 * lane + 4 * (lane >> 2));   // padF(16*lane)
