@@ -729,14 +729,14 @@ def main():
 
 
 def kernel_source_sha():
-    """hash of every kernel source of the library: keys the ncu-derived numbers in profiles/r2_traffic.json"""
-    import glob
+    """hash of the sources of the three kernels of the recognise step (K0 vad, K1 mfcc, K2 dtw) and of what they include:
+    keys the ncu-derived numbers in profiles/r2_traffic.json (host-side files may change without invalidating a capture)"""
     import hashlib
     hsh = hashlib.sha256()
     d = os.path.join(ROOT, "stm32-speech-recognition_b200", "csrc")
-    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(d, "*.h"))):
-        hsh.update(os.path.basename(f).encode())
-        hsh.update(open(f, "rb").read())
+    for name in ("sr_common.cuh", "sr_vad_core.cuh", "sr_vad.cu", "sr_mfcc.cu", "sr_dtw.cu", "sr_tables.cu", "sr_tables.h"):
+        hsh.update(name.encode())
+        hsh.update(open(os.path.join(d, name), "rb").read())
     return hsh.hexdigest()[:16]
 
 

@@ -11,6 +11,9 @@
 #include "sr_numa.h"
 #include <map>
 
+#ifndef SR_COPY_STREAMS_DEFAULT
+#define SR_COPY_STREAMS_DEFAULT 1
+#endif
 #ifndef SR_TRANSPORT_AUTO_DEFAULT
 #define SR_TRANSPORT_AUTO_DEFAULT 1      // what mode -1 (automatic) means: 1 = pack when this rank's share of the CPUs is >= 6
 #endif
@@ -60,6 +63,7 @@ int sr_create(int device, sr_handle **out) {
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     h->stream = h->own_stream;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming | cudaEventBlockingSync);   // the packed transport's sender sleeps on it
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -83,6 +87,7 @@ int sr_destroy(sr_handle *h) {
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
     for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     delete h;
     return 0;
@@ -546,7 +551,9 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         const uint32_t b0 = c * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
         const size_t ns = (size_t)nb * U;
         u16 *dpcm = reinterpret_cast<u16 *>(static_cast<unsigned char *>(h->pcm.p) + (size_t)buf * chunk_bytes);
-        cudaStream_t cs = nchunks > 1 ? h->copy_stream : h->stream;
+        // SR_COPY_STREAMS=2: the two device buffers are fed from two copy streams (two copy engines in flight at once)
+        static const int n_cs = [] { const char *e = getenv("SR_COPY_STREAMS"); const int v = e ? atoi(e) : SR_COPY_STREAMS_DEFAULT; return v == 2 ? 2 : 1; }();
+        cudaStream_t cs = nchunks > 1 ? ((n_cs == 2 && buf) ? h->copy_stream2 : h->copy_stream) : h->stream;
         if (nchunks > 1 && h->chunk_seq >= 2) SR_CK(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));      // buffers free again
         if (packed_src) {
             unsigned char *dpk = static_cast<unsigned char *>(h->dpacked.p) + (size_t)buf * h->stage_cap;
@@ -585,8 +592,10 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     const bool tauto = tmode < 0;
     bool packed_transport = tmode > 0 || (tauto && transport_auto_pick(h));
     const auto t_call0 = std::chrono::steady_clock::now();
+    bool did_setup = false;                              // this call created the pool / staging: its time is not a measurement
     if (packed_transport) {                              // workers, pinned staging slots, device staging
         const size_t pk = ((((size_t)chunk * U + 1) / 2 * 3 + 64 + 255) / 256) * 256;
+        did_setup = !h->pool || h->stage_cap < pk || h->dpacked.cap < 2 * pk;
         ScopedNodeAffinity node_scope(h->numa_node);      // workers inherit it; staging pages are allocated from this node
         if (!h->pool) {
             // packers = this rank's CPU share minus room for the sender, the CUDA runtime's threads and the caller's own work
@@ -683,7 +692,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         { std::lock_guard<std::mutex> lk(m); abort = true; }
         cv_slot.notify_all();
         packer.join();
-        if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
+        if (rc) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->copy_stream2); return rc; }
     }
     if (o->atap) D2H(h, o->atap, d.atap, (size_t)B * sizeof(atap_tag));
     if (o->seg_off) D2H(h, o->seg_off, d.seg_off, (size_t)B * 24);
@@ -697,7 +706,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     if (o->cmd) D2H(h, o->cmd, d.cmd, (size_t)B * 4);
     if (o->status) D2H(h, o->status, d.status, (size_t)B);
     SR_CK(h, cudaStreamSynchronize(h->stream));
-    if (tauto)
+    if (tauto && !did_setup)
         transport_auto_record(h, packed_transport && h->last_packed > 0,
                               std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_call0).count() / ((double)B * U * 2.0));
     return 0;

@@ -58,6 +58,7 @@ struct sr_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                 // H2D of the next chunk while the current one computes
+    cudaStream_t copy_stream2 = nullptr;                // optional second copy stream (SR_COPY_STREAMS=2)
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
     std::string err;
