@@ -460,6 +460,9 @@ def main():
         w["seg"] = torch.zeros((Bw, 6), dtype=torch.int32, device=dev)
         w["ftr"] = torch.zeros((Bw, 2860), dtype=torch.uint8, device=dev)
         w["score"] = torch.zeros((Bw, Tw), dtype=torch.int32, device=dev)
+        # N > 1: two score buffers used in turn, so that the template scan of step i+1 never waits for the gather of step i
+        w["score_alt"] = torch.zeros((Bw, Tw), dtype=torch.int32, device=dev) if world > 1 else None
+        w["k"] = 0
         w["bidx"] = torch.zeros(Bw, dtype=torch.int32, device=dev)
         w["bdis"] = torch.zeros(Bw, dtype=torch.int32, device=dev)
         w["cmd"] = torch.zeros(Bw, dtype=torch.int32, device=dev)
@@ -475,9 +478,13 @@ def main():
         h.set_bank_dev(w["bank"].data_ptr(), w["T"], 4096)
         if world > 1:
             # spch_recg on this rank's shard + the one exchange step of the path: NCCL all-gather of the u32
-            # scores and the 8-byte argmin keys, on the communicator's own stream: it overlaps the next step's VAD/MFCC
+            # scores and the 8-byte argmin keys, on the communicator's own stream: it overlaps the next step entirely
+            outs = dict(w["outs"])
+            w["last_score"] = w["score_alt"] if (w["k"] & 1) else w["score"]
+            outs["score"] = w["last_score"].data_ptr()
+            w["k"] += 1
             h.recognise_dev_allgather(w["pcm"].data_ptr(), U, w["B"], N_LEN, gathered_score=w["gathered"].data_ptr(),
-                                      gathered_best=w["gbest"].data_ptr(), **w["outs"])
+                                      gathered_best=w["gbest"].data_ptr(), **outs)
         else:
             h.recognise_dev(w["pcm"].data_ptr(), U, w["B"], N_LEN, **w["outs"])
 
@@ -525,7 +532,7 @@ def main():
         sampler.start()
     ms_step, recs, launches = timed_pass(w, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    pcm, bank, seg, ftr, score = w["pcm"], w["bank"], w["seg"], w["ftr"], w["score"]
+    pcm, bank, seg, ftr, score = w["pcm"], w["bank"], w["seg"], w["ftr"], w.get("last_score", w["score"])
     bidx, bdis, cmd, status = w["bidx"], w["bdis"], w["cmd"], w["status"]
 
     # the exchange step's result must be the ranks' results in rank order

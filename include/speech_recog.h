@@ -295,9 +295,11 @@ int sr_debug_sqrt_mismatches(sr_handle *h, uint32_t lo_bits, uint32_t hi_bits, u
  * device; chunks with any larger sample travel as plain u16, so results never change. The caller's thread keeps
  * sending plain chunks from the front of the batch while the workers pack from the back, so the call is never slower
  * than the plain transport and approaches 3/4 of its PCIe time as the CPU share grows. mode: 0 off, 1 on,
- * -1 automatic = the default: on when this rank's share of the usable CPUs (affinity capped by the cgroup quota,
- * divided by LOCAL_WORLD_SIZE) is >= 6 and the batch has >= 4 chunks; SR_PACK12=0|1 overrides the automatic choice,
- * SR_PACK_THREADS the worker count (default: CPU share - 3, at most 16). */
+ * -1 automatic = the default: considered when this rank's share of the usable CPUs (affinity capped by the cgroup quota,
+ * divided by LOCAL_WORLD_SIZE) is >= 6, at most two ranks share the box and the batch has >= 4 chunks; the library then
+ * MEASURES: one call plain, one packed, afterwards whichever is clearly faster, the other re-probed every 32nd call
+ * (packing gains ~16 % with one GPU per socket and loses with four). SR_PACK12=0|1 overrides the automatic choice,
+ * SR_PACK_THREADS the worker count (default: CPU share - 3, at most 10). */
 int sr_set_transport(sr_handle *h, int mode);
 /* transport statistics of the last sr_recognise_batch call: chunks sent packed / plain, bytes copied host -> device */
 int sr_transport_stats(const sr_handle *h, uint32_t *packed_chunks, uint32_t *plain_chunks, uint64_t *h2d_bytes);

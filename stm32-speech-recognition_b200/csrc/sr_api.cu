@@ -11,9 +11,6 @@
 #include "sr_numa.h"
 #include <map>
 
-#ifndef SR_COPY_STREAMS_DEFAULT
-#define SR_COPY_STREAMS_DEFAULT 1
-#endif
 #ifndef SR_TRANSPORT_AUTO_DEFAULT
 #define SR_TRANSPORT_AUTO_DEFAULT 1      // what mode -1 (automatic) means: 1 = pack when this rank's share of the CPUs is >= 6
 #endif
@@ -63,7 +60,6 @@ int sr_create(int device, sr_handle **out) {
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     h->stream = h->own_stream;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming | cudaEventBlockingSync);   // the packed transport's sender sleeps on it
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -81,13 +77,12 @@ int sr_destroy(sr_handle *h) {
     sr_comm_destroy(h);
     delete h->pool;
     for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
-    DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->status,
+    DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->best_alt, &h->status,
                       &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2, &h->dtw_scratch};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
     for (int i = 0; i < 2; ++i) { if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     delete h;
     return 0;
@@ -296,8 +291,9 @@ static int dtw_dev_impl(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t 
     const bool want_best = best_idx || best_dis || cmd;
     u64 *best = nullptr;
     if (want_best) {
-        SR_CK(h, ensure(h->best, (size_t)B * 8));
-        best = static_cast<u64 *>(h->best.p);
+        DevBuf &bb = h->best_sel ? h->best_alt : h->best;
+        SR_CK(h, ensure(bb, (size_t)B * 8));
+        best = static_cast<u64 *>(bb.p);
         { TimedLaunch tl(h, TAG_BEST_INIT); SR_CK(h, launch_best_init(best, B, h->stream)); }
         ++h->launches;
     }
@@ -359,7 +355,10 @@ int recognise_dev_impl(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, pcm, U, B, seg, 6, atap, ftr)); }
     { TimedLaunch tl(h, TAG_STATUS); SR_CK(h, launch_status(seg, ftr, B, status, h->stream)); }
     h->launches += 3;
-    if (wait_comm) { const int rc = sr_comm_wait(h); if (rc) return rc; }
+    if (h->comm) {                                       // collectives of earlier calls may still read score / the key buffer
+        const int rc = wait_comm ? comm_wait_before_scan(h, o->score) : sr_comm_wait(h);
+        if (rc) return rc;
+    }
     // main.c:276-294 template scan, argmin, command index
     return dtw_dev_impl(h, ftr, B, SR_DTW_CHECK_SIGN, 0, o->score, o->best_idx, o->best_dis, o->cmd, status);
 }
@@ -448,12 +447,13 @@ int sr_dtw_batch(sr_handle *h, const v_ftr_tag *in, uint32_t B, uint32_t flags, 
     return 0;
 }
 
-// CPUs this rank may count on: the process' usable CPUs (affinity capped by the cgroup quota) divided by the ranks that
-// share them (torchrun exports LOCAL_WORLD_SIZE)
-static int rank_cpu_share() {
+// ranks of this node that share the host (torchrun exports LOCAL_WORLD_SIZE)
+static int local_world_size() {
     static const int local_world = [] { const char *e = getenv("LOCAL_WORLD_SIZE"); const int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();
-    return usable_cpus() / local_world;
+    return local_world;
 }
+// CPUs this rank may count on: the process' usable CPUs (affinity capped by the cgroup quota) divided by those ranks
+static int rank_cpu_share() { return usable_cpus() / local_world_size(); }
 
 // 1 = forced on, 0 = forced off, -1 = automatic (decided per call by transport_auto_pick)
 static int transport_mode(const sr_handle *h) {
@@ -462,7 +462,10 @@ static int transport_mode(const sr_handle *h) {
         static const int env_mode = [] { const char *e = getenv("SR_PACK12"); return e && *e ? atoi(e) : -1; }();
         mode = env_mode;
     }
-    if (mode < 0 && !(SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6)) mode = 0;
+    // automatic: needs CPUs to pack with, and at most two ranks on the box (with three or more GPUs per socket the DMA reads
+    // alone saturate the socket's DRAM bandwidth: packing measured 25.8 vs 19.5 ms at 4 and 8 ranks, and ranks that probe
+    // at different moments talk each other into it)
+    if (mode < 0 && !(SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6 && local_world_size() <= 2)) mode = 0;
     return mode;
 }
 
@@ -470,12 +473,13 @@ static int transport_mode(const sr_handle *h) {
 // one or two ranks per socket gain ~16 % (16.3 vs 19.4 ms per 1.05 GB), but with four ranks per socket the DMA reads
 // alone take ~216 GB/s of that socket's DRAM bandwidth and the packers' extra traffic makes the call SLOWER (25.8 vs
 // 19.5 ms, measured at 4 and 8 GPUs). So: the first qualifying call goes plain, the second packed, then the faster of
-// the two (ns per byte, exponentially averaged) is used, with the other re-probed every 32nd call.
+// the two (ns per byte, exponentially averaged; packing must win by 7 %) is used, with the other re-probed every 32nd call.
+// With more than two ranks on the box the automatic mode stays plain (transport_mode above).
 static bool transport_auto_pick(sr_handle *h) {
     const uint64_t n = h->auto_calls++;
     if (h->auto_ns_per_byte[0] <= 0.0) return false;
     if (h->auto_ns_per_byte[1] <= 0.0) return true;
-    const bool packed_better = h->auto_ns_per_byte[1] < h->auto_ns_per_byte[0];
+    const bool packed_better = h->auto_ns_per_byte[1] < 0.93 * h->auto_ns_per_byte[0];   // a clear win only (N = 1: 0.84)
     if (n % 32 == 31) return !packed_better;                       // probe the loser now and then: conditions change
     return packed_better;
 }
@@ -551,9 +555,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         const uint32_t b0 = c * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
         const size_t ns = (size_t)nb * U;
         u16 *dpcm = reinterpret_cast<u16 *>(static_cast<unsigned char *>(h->pcm.p) + (size_t)buf * chunk_bytes);
-        // SR_COPY_STREAMS=2: the two device buffers are fed from two copy streams (two copy engines in flight at once)
-        static const int n_cs = [] { const char *e = getenv("SR_COPY_STREAMS"); const int v = e ? atoi(e) : SR_COPY_STREAMS_DEFAULT; return v == 2 ? 2 : 1; }();
-        cudaStream_t cs = nchunks > 1 ? ((n_cs == 2 && buf) ? h->copy_stream2 : h->copy_stream) : h->stream;
+        cudaStream_t cs = nchunks > 1 ? h->copy_stream : h->stream;
         if (nchunks > 1 && h->chunk_seq >= 2) SR_CK(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));      // buffers free again
         if (packed_src) {
             unsigned char *dpk = static_cast<unsigned char *>(h->dpacked.p) + (size_t)buf * h->stage_cap;
@@ -692,7 +694,7 @@ int sr_recognise_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
         { std::lock_guard<std::mutex> lk(m); abort = true; }
         cv_slot.notify_all();
         packer.join();
-        if (rc) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->copy_stream2); return rc; }
+        if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
     }
     if (o->atap) D2H(h, o->atap, d.atap, (size_t)B * sizeof(atap_tag));
     if (o->seg_off) D2H(h, o->seg_off, d.seg_off, (size_t)B * 24);

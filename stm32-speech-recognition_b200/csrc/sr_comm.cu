@@ -70,8 +70,12 @@ struct sr_comm {
     ncclComm_p comm = nullptr;
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;                                  // the collective's own stream
-    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;              // producer finished / gather finished
-    bool pending = false;
+    cudaEvent_t ev_ready = nullptr;                                 // producer finished
+    // The last two collectives. A recognise call alternates the handle's internal key buffer (best / best_alt) and a caller
+    // that alternates its score buffers too never makes the template scan wait for the PREVIOUS batch's gather: the scan
+    // only waits for the gather that last read the buffers it is about to rewrite -- two calls back, long finished.
+    struct Slot { cudaEvent_t ev_done = nullptr; const void *score = nullptr; bool pending = false; } slot[2];
+    int next = 0;                                                   // slot (= key buffer) of the call being issued
 };
 
 extern "C" {
@@ -101,7 +105,7 @@ int sr_comm_destroy(sr_handle *h) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl_api()->CommDestroy(c->comm);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
-    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    for (auto &sl : c->slot) if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     h->comm = nullptr;
@@ -124,7 +128,7 @@ int sr_comm_create(sr_handle *h, int rank, int world, const void *id128) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    for (auto &sl : c->slot) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { sr_comm_destroy(h); return fail(h, "sr_comm_create: stream/event", e); }
     ncclUniqueId_t id;
     memcpy(&id, id128, sizeof id);
@@ -138,7 +142,8 @@ int sr_comm_world(const sr_handle *h) { return h && h->comm ? h->comm->world : 1
 
 // up to two all-gathers of equal blocks as ONE NCCL group (one kernel): recv[r*bytes .. ) = rank r's send block. Ordered
 // after everything issued so far on the handle's stream; runs on the communicator's stream.
-static int allgather2(sr_handle *h, const void *send0, void *recv0, size_t bytes0, const void *send1, void *recv1, size_t bytes1) {
+static int allgather2(sr_handle *h, const void *send0, void *recv0, size_t bytes0, const void *send1, void *recv1, size_t bytes1,
+                      const void *score_tag) {
     sr_comm *c = h->comm;
     NcclApi *a = nccl_api();
     SR_CK(h, cudaEventRecord(c->ev_ready, h->stream));
@@ -150,8 +155,10 @@ static int allgather2(sr_handle *h, const void *send0, void *recv0, size_t bytes
     if (!rc && bytes1) rc = a->AllGather(send1, recv1, bytes1, kNcclUint8, c->comm, c->stream);
     if (group) { const int rc2 = a->GroupEnd(); if (!rc) rc = rc2; }
     if (rc) return nccl_fail(h, "ncclAllGather", rc);
-    SR_CK(h, cudaEventRecord(c->ev_done, c->stream));
-    c->pending = true;
+    sr_comm::Slot &sl = c->slot[c->next];
+    SR_CK(h, cudaEventRecord(sl.ev_done, c->stream));
+    sl.pending = true; sl.score = score_tag;
+    c->next ^= 1;
     return 0;
 }
 
@@ -160,18 +167,38 @@ int sr_allgather_dev(sr_handle *h, const void *send, void *recv, size_t bytes_pe
     SR_REQUIRE(h, h && h->comm && (bytes_per_rank == 0 || (send && recv)));
     if (bytes_per_rank == 0) return 0;
     DeviceGuard g(h->device);
-    return allgather2(h, send, recv, bytes_per_rank, nullptr, nullptr, 0);
+    return allgather2(h, send, recv, bytes_per_rank, nullptr, nullptr, 0, send);
 }
 
 // make the handle's stream wait for the collectives issued so far (then sr_sync / stream order covers them)
 int sr_comm_wait(sr_handle *h) {
     SR_REQUIRE(h, h != nullptr);
-    if (!h->comm || !h->comm->pending) return 0;
+    if (!h->comm) return 0;
     DeviceGuard g(h->device);
-    SR_CK(h, cudaStreamWaitEvent(h->stream, h->comm->ev_done, 0));
-    h->comm->pending = false;
+    for (auto &sl : h->comm->slot)
+        if (sl.pending) { SR_CK(h, cudaStreamWaitEvent(h->stream, sl.ev_done, 0)); sl.pending = false; }
     return 0;
 }
+
+}  // extern "C"
+
+// Before the template scan of a recognise call rewrites score / best: wait for the gathers that may still read them -- the
+// one in the slot this call will reuse (it read the same key buffer, two calls ago) and any that read the same score buffer.
+int comm_wait_before_scan(sr_handle *h, const void *score) {
+    sr_comm *c = h->comm;
+    if (!c) return 0;
+    h->best_sel = c->next;
+    for (int i = 0; i < 2; ++i) {
+        sr_comm::Slot &sl = c->slot[i];
+        if (sl.pending && (i == c->next || (score && sl.score == score))) {
+            SR_CK(h, cudaStreamWaitEvent(h->stream, sl.ev_done, 0));
+            sl.pending = false;
+        }
+    }
+    return 0;
+}
+
+extern "C" {
 
 // spch_recg for this rank's shard + the exchange step: gathered_score[world*B][n_slot] (u32, rank-major = global
 // utterance order for equal shards) and/or gathered_best[world*B] = (best_dis << 32 | best_idx), the key of the
@@ -187,13 +214,15 @@ int sr_recognise_batch_dev_allgather(sr_handle *h, const uint16_t *pcm, uint32_t
         SR_CK(h, ensure(h->bidx, (size_t)B * 4));
         o.best_idx = static_cast<u32 *>(h->bidx.p);
     }
-    // The previous batch's gather may still be reading score / best. Only the template scan rewrites them, so only it waits
-    // (inside recognise_dev_impl): this batch's VAD and MFCC overlap the previous gather.
+    // A gather issued earlier may still be reading score / best. Only the template scan rewrites them, so only it waits
+    // (comm_wait_before_scan inside recognise_dev_impl) -- and with alternating buffers it waits for the gather of two calls
+    // ago, so nothing on the handle's stream ever waits for the previous batch's collective.
     int rc = recognise_dev_impl(h, pcm, U, B, n_len, &o, true);
     if (rc) return rc;
     if (!gathered_score && !gathered_best) return 0;
+    const void *keys = h->best_sel ? h->best_alt.p : h->best.p;     // the buffer this call's template scan just filled
     return allgather2(h, gathered_score ? o.score : nullptr, gathered_score, gathered_score ? (size_t)B * h->n_slot * 4 : 0,
-                      gathered_best ? h->best.p : nullptr, gathered_best, gathered_best ? (size_t)B * 8 : 0);
+                      gathered_best ? keys : nullptr, gathered_best, gathered_best ? (size_t)B * 8 : 0, o.score);
 }
 
 }  // extern "C"

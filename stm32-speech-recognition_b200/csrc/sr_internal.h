@@ -58,7 +58,6 @@ struct sr_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                 // H2D of the next chunk while the current one computes
-    cudaStream_t copy_stream2 = nullptr;                // optional second copy stream (SR_COPY_STREAMS=2)
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
     std::string err;
@@ -91,7 +90,9 @@ struct sr_handle {
     int geom = 0;                                      // SR_GEOM_REF (160/80/1024) or SR_GEOM_B (200/80/256, extension)
     int numa_node = -1;                                // node the device hangs off (-1 unknown / single node)
     // grow-only device workspaces
-    DevBuf pcm, atap, seg, ftr, score, best, status, bidx, bdis, cmd, misc0, misc1, misc2;
+    DevBuf pcm, atap, seg, ftr, score, best, best_alt, status, bidx, bdis, cmd, misc0, misc1, misc2;
+    int best_sel = 0;                                  // which of best / best_alt the current recognise call uses (alternates when a
+                                                       // communicator is attached: the previous call's keys may still be being gathered)
 };
 
 inline int fail(sr_handle *h, const char *what, cudaError_t e) {
@@ -148,6 +149,7 @@ inline cudaError_t launch_dtw_h(sr_handle *h, const void *in_ftr, u32 B, u32 fla
     return launch_dtw(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream, B_dev);
 }
 
+int comm_wait_before_scan(sr_handle *h, const void *score);   // sr_comm.cu
 int recognise_dev_impl(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, uint32_t n_len, const sr_recog_out *o,
                        bool wait_comm);             // sr_api.cu
 
