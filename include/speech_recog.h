@@ -296,8 +296,8 @@ int sr_debug_sqrt_mismatches(sr_handle *h, uint32_t lo_bits, uint32_t hi_bits, u
  * sending plain chunks from the front of the batch while the workers pack from the back, so the call is never slower
  * than the plain transport and approaches 3/4 of its PCIe time as the CPU share grows. mode: 0 off, 1 on,
  * -1 automatic = the default: considered when this rank's share of the usable CPUs (affinity capped by the cgroup quota,
- * divided by LOCAL_WORLD_SIZE) is >= 6, at most two ranks share the box and the batch has >= 4 chunks; the library then
- * MEASURES: one call plain, one packed, afterwards whichever is clearly faster, the other re-probed every 32nd call
+ * divided by LOCAL_WORLD_SIZE) is >= 6, no other local rank's GPU hangs off the same NUMA node and the batch has >= 4
+ * chunks; the library then MEASURES: one call plain, one packed, afterwards whichever is clearly faster, the other re-probed every 32nd call
  * (packing gains ~16 % with one GPU per socket and loses with four). SR_PACK12=0|1 overrides the automatic choice,
  * SR_PACK_THREADS the worker count (default: CPU share - 3, at most 10). */
 int sr_set_transport(sr_handle *h, int mode);

@@ -10,6 +10,7 @@
 #include "sr_pack_host.h"
 #include "sr_numa.h"
 #include <map>
+#include <algorithm>
 
 #ifndef SR_TRANSPORT_AUTO_DEFAULT
 #define SR_TRANSPORT_AUTO_DEFAULT 1      // what mode -1 (automatic) means: 1 = pack when this rank's share of the CPUs is >= 6
@@ -78,7 +79,7 @@ int sr_destroy(sr_handle *h) {
     delete h->pool;
     for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
     DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->best_alt, &h->status,
-                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2, &h->dtw_scratch};
+                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2, &h->dtw_scratch, &h->bank_perm, &h->vad_work};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -207,12 +208,40 @@ int sr_timing_collect(sr_handle *h, uint32_t *tags, float *ms, uint32_t cap, uin
 }
 
 // ---- template bank --------------------------------------------------------------------------------
+// Banks wider than one 32-template tile are walked in ascending frm_num order, so that the templates sharing a warp have
+// similar walk lengths (CPU model: mean/max walk length per tile 0.81 -> 0.88 at T = 200). The order is a hint: scores and
+// argmin keys carry the original slot numbers, and a stale order (bank rewritten in place) only costs efficiency.
+static int bank_order(sr_handle *h, const unsigned char *hdr_host /* n_slot headers, 4 bytes each, or NULL: fetch */) {
+    h->perm = nullptr;
+    const u32 T = h->n_slot;
+    if (T <= 32 || !h->bank) { h->perm_bank = h->bank; h->perm_n = T; h->perm_stride = h->slot_stride; return 0; }
+    std::vector<u32> hdr(T);
+    if (hdr_host) memcpy(hdr.data(), hdr_host, (size_t)T * 4);
+    else {
+        SR_CK(h, cudaMemcpy2DAsync(hdr.data(), 4, h->bank, h->slot_stride, 4, T, cudaMemcpyDeviceToHost, h->stream));
+        SR_CK(h, cudaStreamSynchronize(h->stream));
+    }
+    std::vector<u32> order(T);
+    for (u32 i = 0; i < T; ++i) order[i] = i;
+    auto key = [&](u32 i) { const u32 f = hdr[i] >> 16; return f > 119u ? 0xFFFFu : f; };   // garbage headers last
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return key(a) < key(b); });
+    SR_CK(h, ensure(h->bank_perm, (size_t)T * 4));
+    SR_CK(h, cudaMemcpyAsync(h->bank_perm.p, order.data(), (size_t)T * 4, cudaMemcpyHostToDevice, h->stream));
+    SR_CK(h, cudaStreamSynchronize(h->stream));                     // `order` is a local
+    h->perm = static_cast<const u32 *>(h->bank_perm.p);
+    h->perm_bank = h->bank; h->perm_n = T; h->perm_stride = h->slot_stride;
+    return 0;
+}
+
 int sr_set_bank_dev(sr_handle *h, const void *bank_dev, uint32_t n_slot, uint32_t slot_stride) {
     SR_REQUIRE(h, h != nullptr);
     SR_REQUIRE(h, n_slot == 0 || (bank_dev != nullptr && slot_stride >= (uint32_t)kFtrBytes && slot_stride % 4 == 0));
     SR_REQUIRE(h, (reinterpret_cast<uintptr_t>(bank_dev) & 3) == 0);
+    const bool same = h->perm_bank == bank_dev && h->perm_n == n_slot && h->perm_stride == slot_stride;
     h->bank = bank_dev; h->n_slot = n_slot; h->slot_stride = slot_stride;
-    return 0;
+    if (same) return 0;                                   // same buffer as last time (callers re-set it per batch): keep the order
+    DeviceGuard g(h->device);
+    return bank_order(h, nullptr);
 }
 int sr_set_bank(sr_handle *h, const void *bank, uint32_t n_slot, uint32_t slot_stride) {
     SR_REQUIRE(h, h != nullptr);
@@ -224,7 +253,9 @@ int sr_set_bank(sr_handle *h, const void *bank, uint32_t n_slot, uint32_t slot_s
     if (bytes) SR_CK(h, cudaMemcpyAsync(h->bank_own.p, bank, bytes, cudaMemcpyHostToDevice, h->stream));
     SR_CK(h, cudaStreamSynchronize(h->stream));
     h->bank = h->bank_own.p; h->n_slot = n_slot; h->slot_stride = slot_stride;
-    return 0;
+    std::vector<u32> hdr(n_slot);
+    for (u32 i = 0; i < n_slot; ++i) memcpy(&hdr[i], static_cast<const unsigned char *>(bank) + (size_t)i * slot_stride, 4);
+    return bank_order(h, reinterpret_cast<const unsigned char *>(hdr.data()));
 }
 
 // ---- command labels: commstr[] of main.c:25-31, what spch_recg returns (main.c:295) ---------------------------------
@@ -258,7 +289,7 @@ int sr_noise_atap_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint3
     SR_REQUIRE(h, h && (B == 0 || (pcm && atap)));
     SR_REQUIRE(h, U <= 65535u && n_len <= 65535u);
     DeviceGuard g(h->device);
-    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, 0, 1, 0, atap, nullptr, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, 0, 1, 0, atap, nullptr, h->num_sms, h->stream, vad_work(h))); }
     h->launches += B ? 1 : 0;
     return 0;
 }
@@ -268,7 +299,7 @@ int sr_vad_batch_dev(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, 
     SR_REQUIRE(h, h && (B == 0 || (pcm && atap && seg_off)));
     SR_REQUIRE(h, U <= 65535u && buf_len <= U);
     DeviceGuard g(h->device);
-    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, 0, buf_len, 0, 1, const_cast<atap_tag *>(atap), seg_off, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, 0, buf_len, 0, 1, const_cast<atap_tag *>(atap), seg_off, h->num_sms, h->stream, vad_work(h))); }
     h->launches += B ? 1 : 0;
     return 0;
 }
@@ -350,7 +381,7 @@ int recognise_dev_impl(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B
     u8 *status = o->status;
     if (!status) { SR_CK(h, ensure(h->status, (size_t)B)); status = static_cast<u8 *>(h->status.p); }
     // main.c:258-260 noise_atap + VAD (one fused launch on the staged utterance)
-    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, U, 1, 1, atap, seg, h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(pcm, U, B, n_len, U, 1, 1, atap, seg, h->num_sms, h->stream, vad_work(h))); }
     // main.c:268 get_mfcc of segment 0
     { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, pcm, U, B, seg, 6, atap, ftr)); }
     { TimedLaunch tl(h, TAG_STATUS); SR_CK(h, launch_status(seg, ftr, B, status, h->stream)); }
@@ -455,6 +486,17 @@ static int local_world_size() {
 // CPUs this rank may count on: the process' usable CPUs (affinity capped by the cgroup quota) divided by those ranks
 static int rank_cpu_share() { return usable_cpus() / local_world_size(); }
 
+// local ranks whose GPU hangs off the same NUMA node as this handle's (torchrun convention: local rank r drives device r);
+// unknown topology counts everybody
+static int ranks_on_socket(const sr_handle *h) {
+    const int W = local_world_size();
+    if (W <= 1) return 1;
+    if (h->numa_node < 0) return W;
+    int n = 0;
+    for (int d = 0; d < W; ++d) if (device_numa_node(d) == h->numa_node) ++n;
+    return n < 1 ? 1 : n;
+}
+
 // 1 = forced on, 0 = forced off, -1 = automatic (decided per call by transport_auto_pick)
 static int transport_mode(const sr_handle *h) {
     int mode = h->transport_mode;
@@ -462,10 +504,10 @@ static int transport_mode(const sr_handle *h) {
         static const int env_mode = [] { const char *e = getenv("SR_PACK12"); return e && *e ? atoi(e) : -1; }();
         mode = env_mode;
     }
-    // automatic: needs CPUs to pack with, and at most two ranks on the box (with three or more GPUs per socket the DMA reads
-    // alone saturate the socket's DRAM bandwidth: packing measured 25.8 vs 19.5 ms at 4 and 8 ranks, and ranks that probe
-    // at different moments talk each other into it)
-    if (mode < 0 && !(SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6 && local_world_size() <= 2)) mode = 0;
+    // automatic: needs CPUs to pack with, and the socket's DRAM bandwidth to itself: with several GPUs per socket the DMA
+    // reads alone load it (4 x 54 GB/s at four) and packing measured 25.8 vs 19.5 ms at 4 and 8 ranks, 19.8-21.3 vs 19.5 with
+    // two ranks on one socket -- and ranks that probe at different moments talk each other into it. One rank per socket only.
+    if (mode < 0 && !(SR_TRANSPORT_AUTO_DEFAULT && rank_cpu_share() >= 6 && ranks_on_socket(h) <= 1)) mode = 0;
     return mode;
 }
 
@@ -474,7 +516,7 @@ static int transport_mode(const sr_handle *h) {
 // alone take ~216 GB/s of that socket's DRAM bandwidth and the packers' extra traffic makes the call SLOWER (25.8 vs
 // 19.5 ms, measured at 4 and 8 GPUs). So: the first qualifying call goes plain, the second packed, then the faster of
 // the two (ns per byte, exponentially averaged; packing must win by 7 %) is used, with the other re-probed every 32nd call.
-// With more than two ranks on the box the automatic mode stays plain (transport_mode above).
+// With more than one rank on this GPU's socket the automatic mode stays plain (transport_mode above).
 static bool transport_auto_pick(sr_handle *h) {
     const uint64_t n = h->auto_calls++;
     if (h->auto_ns_per_byte[0] <= 0.0) return false;
@@ -731,7 +773,7 @@ int sr_enrol_batch(sr_handle *h, const uint16_t *pcm, uint32_t U, uint32_t B, ui
     SR_CK(h, ensure(h->misc0, (size_t)B * slot_stride));
     H2D(h, h->pcm.p, pcm, (size_t)B * U * 2);
     SR_CK(h, cudaMemsetAsync(h->atap.p, 0, (size_t)B * sizeof(atap_tag), h->stream));
-    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(static_cast<const u16 *>(h->pcm.p), U, B, n_len, U, 1, 1, static_cast<atap_tag *>(h->atap.p), static_cast<u32 *>(h->seg.p), h->num_sms, h->stream)); }
+    { TimedLaunch tl(h, TAG_VAD); SR_CK(h, launch_vad(static_cast<const u16 *>(h->pcm.p), U, B, n_len, U, 1, 1, static_cast<atap_tag *>(h->atap.p), static_cast<u32 *>(h->seg.p), h->num_sms, h->stream, vad_work(h))); }
     { TimedLaunch tl(h, TAG_MFCC); SR_CK(h, launch_mfcc_h(h, static_cast<const u16 *>(h->pcm.p), U, B, static_cast<const u32 *>(h->seg.p), 6, static_cast<const atap_tag *>(h->atap.p), h->ftr.p)); }
     SR_CK(h, launch_status(static_cast<const u32 *>(h->seg.p), h->ftr.p, B, static_cast<u8 *>(h->status.p), h->stream));
     SR_CK(h, launch_pack_slots(h->ftr.p, static_cast<const u8 *>(h->status.p), B, h->misc0.p, slot_stride, h->stream));
@@ -943,13 +985,15 @@ uint32_t dtw(v_ftr_tag *ftr_in, v_ftr_tag *frt_mdl) {
     if (!h || !ftr_in || !frt_mdl) return SR_DIS_ERR;
     g_last_I = ftr_in->frm_num; g_last_M = frt_mdl->frm_num;                  // DTW.C:130-131
     const void *sv_bank = h->bank; const u32 sv_n = h->n_slot, sv_s = h->slot_stride;
+    const u32 *sv_perm = h->perm;
     uint32_t score = SR_DIS_ERR;
     DeviceGuard g(h->device);
     if (ensure(h->misc2, kFtrBytes + 16) != cudaSuccess) return SR_DIS_ERR;
     if (cudaMemcpyAsync(h->misc2.p, frt_mdl, kFtrBytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return SR_DIS_ERR;
     h->bank = h->misc2.p; h->n_slot = 1; h->slot_stride = kFtrBytes;
+    h->perm = nullptr;                                              // the slot order belongs to the handle's real bank
     const int rc = sr_dtw_batch(h, ftr_in, 1, 0, 0, &score, nullptr, nullptr);
-    h->bank = sv_bank; h->n_slot = sv_n; h->slot_stride = sv_s;
+    h->bank = sv_bank; h->n_slot = sv_n; h->slot_stride = sv_s; h->perm = sv_perm;
     return rc == 0 ? score : SR_DIS_ERR;
 }
 

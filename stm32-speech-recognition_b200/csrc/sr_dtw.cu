@@ -79,7 +79,9 @@ dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char 
            u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best,
            const u8 *__restrict__ status /* may be NULL: per-utterance SR_ST_* gate of sr_recognise */,
            int Wg, int NU, int G, u32 tile0, int tslots /* template slots allocated in shared memory */,
-           const u32 *__restrict__ B_dev /* optional: batch size produced on the device (streaming) */) {
+           const u32 *__restrict__ B_dev /* optional: batch size produced on the device (streaming) */,
+           const u32 *__restrict__ perm /* optional: bank slots in ascending frm_num order (templates of a tile then have
+                                           similar walk lengths); results are indexed by the ORIGINAL slot number */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (B_dev) B = min(B, *B_dev);
     if (B == 0) return;
@@ -87,20 +89,21 @@ dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char 
     const u32 t0 = (blockIdx.x + tile0) * kTileT;
     const int Tt = (int)min((u32)kTileT, T - t0);
     unsigned char *tile = smem_raw;                                   // Tt slots
-    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)tslots * kSlotBytes);   // [32]
-    unsigned char *uslots = smem_raw + (size_t)tslots * kSlotBytes + 128;          // G*NU slots
+    u32 *tfrm = reinterpret_cast<u32 *>(smem_raw + (size_t)tslots * kSlotBytes);   // [32] frame counts, then [32] bank slot numbers
+    unsigned char *uslots = smem_raw + (size_t)tslots * kSlotBytes + 256;          // G*NU slots
     u32 *ufrm = reinterpret_cast<u32 *>(uslots + (size_t)G * NU * kSlotBytes);     // [G*NU]
 
     // ---- template tile: byte-plane rows + norms + frame counts ----------------------------------------
     for (int tt = warp; tt < Tt; tt += kK2Warps) {
-        const unsigned char *slot = bank + (size_t)(t0 + tt) * slot_stride;
+        const u32 ts = perm ? perm[t0 + tt] : t0 + (u32)tt;
+        const unsigned char *slot = bank + (size_t)ts * slot_stride;
         const u32 hdr = *reinterpret_cast<const u32 *>(slot);
         u32 frm = hdr >> 16;
         if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;   // main.c:283
         if (frm > 119u && frm != 0xFFFFFFFFu) frm = 0xFFFFFFFEu;                                    // garbage header: no walk
         const int nrows = (frm >= 0xFFFFFFFEu) ? 0 : (int)min(max(frm + 1u, 2u), 119u);   // +1: the do-while may touch row frm; rows 0 and 1 are always read (DTW.C:146-160), also when frm_num == 0
         stage_planes(tile + (size_t)tt * kSlotBytes, slot, nrows, lane, 32);
-        if (lane == 0) tfrm[tt] = frm;
+        if (lane == 0) { tfrm[tt] = frm; tfrm[32 + tt] = ts; }
     }
     __syncthreads();
 
@@ -113,7 +116,7 @@ dtw_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned char 
     u32 *gfrm = ufrm + group * NU;
     const unsigned char *trow = tile + (size_t)tl * kSlotBytes;
     const u32 Mraw = lane_has_pair ? tfrm[tl] : 0xFFFFFFFFu;
-    const u32 t = t0 + (u32)tl;
+    const u32 t = lane_has_pair ? tfrm[32 + tl] : 0u;                  // original slot number: score column and argmin key
 
     for (u32 ubase = (blockIdx.y * G + group) * NU; ubase < B; ubase += gridDim.y * G * NU) {
         // ---- stage NU utterances of this group ---------------------------------------------------------
@@ -323,9 +326,9 @@ __global__ void get_dis_kernel(const s16 *a, const s16 *b, u32 n, u32 *out) {
 // one launch for `ntiles` template tiles of width Tt starting at tile `tile0`
 static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags,
                                     u32 *score, u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 tile0,
-                                    u32 ntiles, int Tt, const u32 *B_dev) {
+                                    u32 ntiles, int Tt, const u32 *B_dev, const u32 *perm) {
     // lane packing: groups of Wg warps walk NU utterances x Tt templates; pick the best (Wg, NU, G)
-    const size_t budget = 224 * 1024 - (size_t)Tt * kSlotBytes - 128 - 512;
+    const size_t budget = 224 * 1024 - (size_t)Tt * kSlotBytes - 256 - 512;
     const int slots_max = (int)(budget / kSlotBytes);
     int bestWg = 1, bestNU = 1, bestG = 1;
     double best_util = -1.0;
@@ -339,7 +342,7 @@ static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank,
         const double util = ((double)NU * Tt / (32.0 * Wg)) * ((double)G * Wg / kK2Warps);
         if (util > best_util + 1e-9) { best_util = util; bestWg = Wg; bestNU = NU; bestG = G; }
     }
-    const size_t smem = (size_t)Tt * kSlotBytes + 128 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
+    const size_t smem = (size_t)Tt * kSlotBytes + 256 + (size_t)bestG * bestNU * kSlotBytes + (size_t)bestG * bestNU * 4 + 64;
     cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     u32 gy = (u32)num_sms / ntiles;                      // floor: one CTA per SM, never a second partial wave
@@ -350,19 +353,19 @@ static cudaError_t launch_dtw_tiles(const void *in_ftr, u32 B, const void *bank,
     dim3 grid(ntiles, gy);
     dtw_kernel<<<grid, kK2Warps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
                                                  static_cast<const unsigned char *>(bank), T, slot_stride, flags,
-                                                 score, best, status, bestWg, bestNU, bestG, tile0, Tt, B_dev);
+                                                 score, best, status, bestWg, bestNU, bestG, tile0, Tt, B_dev, perm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
-                       u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev) {
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev, const u32 *perm) {
     if (B == 0 || T == 0) return cudaSuccess;
     const u32 full = T / kTileT, rem = T % kTileT;
     if (full) {
-        cudaError_t e = launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, kTileT, B_dev);
+        cudaError_t e = launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, kTileT, B_dev, perm);
         if (e != cudaSuccess) return e;
     }
-    if (rem) return launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, (int)rem, B_dev);
+    if (rem) return launch_dtw_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, (int)rem, B_dev, perm);
     return cudaSuccess;
 }
 cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st) {

@@ -95,6 +95,7 @@ struct DynCtrl {
     u32 tmax;
     u32 pad[2];
     u32 tfrm[32];
+    u32 tslot_id[32];
     u32 flag[kDynRMax];
     u32 done[kDynRMax];
     u32 ufrm[kDynRMax];
@@ -107,7 +108,7 @@ dtw_dyn_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned c
                u32 slot_stride, u32 flags, u32 *__restrict__ score, u64 *__restrict__ best,
                const u8 *__restrict__ status, u32 tile0, u32 smem_bytes,
                const u32 *__restrict__ max_frm_dev /* max frm_num over the inputs, or NULL (assume 119) */,
-               const u32 *__restrict__ B_dev) {
+               const u32 *__restrict__ B_dev, const u32 *__restrict__ perm /* optional bank order, see sr_dtw.cu */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DynCtrl &c = *reinterpret_cast<DynCtrl *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,7 +122,9 @@ dtw_dyn_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned c
     for (int i = threadIdx.x; i < kDynRMax; i += blockDim.x) { c.flag[i] = 0; c.done[i] = 0; }
     __syncthreads();
     if (threadIdx.x < Tt) {
-        const u32 hdr = *reinterpret_cast<const u32 *>(bank + (size_t)(t0 + threadIdx.x) * slot_stride);
+        const u32 ts = perm ? perm[t0 + threadIdx.x] : t0 + threadIdx.x;
+        c.tslot_id[threadIdx.x] = ts;
+        const u32 hdr = *reinterpret_cast<const u32 *>(bank + (size_t)ts * slot_stride);
         u32 frm = hdr >> 16;
         if ((flags & SR_DTW_CHECK_SIGN) && (hdr & 0xFFFFu) != SR_SAVE_MASK) frm = 0xFFFFFFFFu;   // main.c:283
         if (frm > 119u && frm != 0xFFFFFFFFu) frm = 0xFFFFFFFEu;                                    // garbage header: no walk
@@ -145,7 +148,7 @@ dtw_dyn_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned c
     for (int tt = warp; tt < Tt; tt += kDynWarps) {
         const u32 frm = c.tfrm[tt];
         const int nrows = (frm >= 0xFFFFFFFEu) ? 0 : (int)min(max(frm + 1u, 2u), 119u);
-        stage_qplanes(tile + (size_t)tt * tslot, tnrm, bank + (size_t)(t0 + tt) * slot_stride, nrows, lane, 32);
+        stage_qplanes(tile + (size_t)tt * tslot, tnrm, bank + (size_t)c.tslot_id[tt] * slot_stride, nrows, lane, 32);
     }
     __syncthreads();
 
@@ -215,7 +218,7 @@ dtw_dyn_kernel(const unsigned char *__restrict__ in_ftr, u32 B, const unsigned c
             slot = pend_seq % R;
             if (ld_acquire_s(&c.flag[slot]) == pend_seq + 1u) {           // staged: start the walk (or reject at once)
                 pending = false;
-                out_u = blockIdx.y + pend_seq * gridDim.y; out_t = t0 + pend_tl;
+                out_u = blockIdx.y + pend_seq * gridDim.y; out_t = c.tslot_id[pend_tl];
                 const u32 Iraw = c.ufrm[slot], Mraw = c.tfrm[pend_tl];
                 I = (int)Iraw; M = (int)Mraw;
                 if (Iraw >= 0xFFFFFFFEu || Mraw >= 0xFFFFFFFEu || I > M * 2 || 2 * I < M) finish(SR_DIS_ERR);       // DTW.C:133
@@ -270,7 +273,7 @@ __global__ void frm_max_kernel(const unsigned char *__restrict__ ftr, u32 B, con
 
 static cudaError_t launch_dyn_tiles(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
                                     u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 tile0, u32 ntiles,
-                                    const u32 *max_frm_dev, const u32 *B_dev) {
+                                    const u32 *max_frm_dev, const u32 *B_dev, const u32 *perm) {
     const u32 smem = 226 * 1024;
     cudaError_t e = cudaFuncSetAttribute(dtw_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -280,13 +283,14 @@ static cudaError_t launch_dyn_tiles(const void *in_ftr, u32 B, const void *bank,
     if (gy > 65535) gy = 65535;
     dtw_dyn_kernel<<<dim3(ntiles, gy), kDynWarps * 32, smem, st>>>(static_cast<const unsigned char *>(in_ftr), B,
                                                                  static_cast<const unsigned char *>(bank), T, slot_stride, flags,
-                                                                 score, best, status, tile0, smem, max_frm_dev, B_dev);
+                                                                 score, best, status, tile0, smem, max_frm_dev, B_dev, perm);
     return cudaGetLastError();
 }
 
 // scratch: one device word for the maximum frame count (owned by the caller's handle)
 cudaError_t launch_dtw_dyn(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
-                           u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 *max_frm_scratch, const u32 *B_dev) {
+                           u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 *max_frm_scratch, const u32 *B_dev,
+                           const u32 *perm) {
     if (B == 0 || T == 0) return cudaSuccess;
     if (max_frm_scratch) {
         cudaError_t e = cudaMemsetAsync(max_frm_scratch, 0, 4, st);
@@ -299,10 +303,10 @@ cudaError_t launch_dtw_dyn(const void *in_ftr, u32 B, const void *bank, u32 T, u
     }
     const u32 full = T / 32u, rem = T % 32u;
     if (full) {
-        cudaError_t e = launch_dyn_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, max_frm_scratch, B_dev);
+        cudaError_t e = launch_dyn_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, 0, full, max_frm_scratch, B_dev, perm);
         if (e != cudaSuccess) return e;
     }
-    if (rem) return launch_dyn_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, max_frm_scratch, B_dev);
+    if (rem) return launch_dyn_tiles(in_ftr, B, bank, T, slot_stride, flags, score, best, status, num_sms, st, full, 1, max_frm_scratch, B_dev, perm);
     return cudaSuccess;
 }
 

@@ -13,7 +13,7 @@
 
 namespace srk {
 cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int do_atap, int do_vad, atap_tag *atap,
-                       u32 *seg_off, int num_sms, cudaStream_t st);
+                       u32 *seg_off, int num_sms, cudaStream_t st, u32 *work = nullptr);
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
                         int num_sms, cudaStream_t st, const u32 *row_map = nullptr, u32 rows_total = 0,
                         const u32 *B_dev = nullptr);
@@ -22,10 +22,11 @@ cudaError_t launch_mfcc_geomb(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
                                cudaStream_t st);
 cudaError_t launch_dtw(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
-                       u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev = nullptr);
+                       u64 *best, const u8 *status, int num_sms, cudaStream_t st, const u32 *B_dev = nullptr,
+                       const u32 *perm = nullptr);
 cudaError_t launch_dtw_dyn(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, u32 *score,
                            u64 *best, const u8 *status, int num_sms, cudaStream_t st, u32 *max_frm_scratch,
-                           const u32 *B_dev = nullptr);
+                           const u32 *B_dev = nullptr, const u32 *perm = nullptr);
 cudaError_t launch_dtw_band(const void *in_ftr, u32 B, const void *bank, u32 T, u32 slot_stride, u32 flags, int band_r,
                             u32 *score, u64 *best, int num_sms, cudaStream_t st);
 cudaError_t launch_best_init(u64 *best, u32 B, cudaStream_t st);
@@ -65,6 +66,12 @@ struct sr_handle {
     const void *bank = nullptr;
     DevBuf bank_own;
     u32 n_slot = 0, slot_stride = 0;
+    // bank slots in ascending frm_num order (only for banks wider than one 32-template tile): an ordering hint for the
+    // greedy dtw kernels, recomputed when the bank pointer / geometry changes; correctness never depends on it
+    DevBuf bank_perm;
+    const u32 *perm = nullptr;
+    const void *perm_bank = nullptr;
+    u32 perm_n = 0, perm_stride = 0;
     // optional per-kernel timing (sr_timing_enable): event pairs recorded around every launch
     bool timing = false;
     std::vector<cudaEvent_t> ev;
@@ -86,6 +93,7 @@ struct sr_handle {
     u32 n_labels = 0, label_stride = 0;
     sr_comm *comm = nullptr;                           // the exchange step (sr_comm_create), optional
     int dtw_variant = -1;                              // greedy dtw kernel: 0 static lane = pair (sr_dtw.cu), 1 dynamic pairs (sr_dtw_dyn.cu), -1 default
+    DevBuf vad_work;                                   // two words: dynamic utterance hand-out of vad_kernel (zeroed once, self re-arming)
     DevBuf dtw_scratch;                                // one word: max frm_num of the current inputs (dynamic kernel's slot size)
     int geom = 0;                                      // SR_GEOM_REF (160/80/1024) or SR_GEOM_B (200/80/256, extension)
     int numa_node = -1;                                // node the device hangs off (-1 unknown / single node)
@@ -129,6 +137,15 @@ inline cudaError_t launch_mfcc_h(sr_handle *h, const u16 *pcm, u32 U, u32 B, con
     return launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, rows_total, B_dev);
 }
 
+// the handle's work counters for vad_kernel (allocated and zeroed on first use)
+inline u32 *vad_work(sr_handle *h) {
+    if (!h->vad_work.p) {
+        if (ensure(h->vad_work, 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaMemsetAsync(h->vad_work.p, 0, 16, h->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    return static_cast<u32 *>(h->vad_work.p);
+}
+
 // greedy dtw of B inputs against the handle's bank with the handle's kernel variant
 #ifndef SR_DTW_VARIANT_DEFAULT
 #define SR_DTW_VARIANT_DEFAULT 0
@@ -144,9 +161,9 @@ inline cudaError_t launch_dtw_h(sr_handle *h, const void *in_ftr, u32 B, u32 fla
         cudaError_t e = ensure(h->dtw_scratch, 16);
         if (e != cudaSuccess) return e;
         return launch_dtw_dyn(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream,
-                              static_cast<u32 *>(h->dtw_scratch.p), B_dev);
+                              static_cast<u32 *>(h->dtw_scratch.p), B_dev, h->perm);
     }
-    return launch_dtw(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream, B_dev);
+    return launch_dtw(in_ftr, B, h->bank, h->n_slot, h->slot_stride, flags, score, best, status, h->num_sms, h->stream, B_dev, h->perm);
 }
 
 int comm_wait_before_scan(sr_handle *h, const void *score);   // sr_comm.cu
