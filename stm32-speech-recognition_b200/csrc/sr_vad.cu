@@ -1,6 +1,7 @@
 // sr_vad.cu -- K0: batched noise_atap (Src/Speech_Recog/VAD.C:22-71) and VAD (VAD.C:97-218).
 //
-// One warp per utterance, persistent grid. A warp's utterances form one stream of 32-block chunks (2560 samples)
+// One warp per utterance, persistent grid, utterances handed out dynamically (one atomic per utterance per warp, so CTAs
+// that start late take fewer). A warp's utterances form one stream of 32-block chunks (2560 samples)
 // through two shared-memory buffers: 1-D bulk async copies (TMA engine) keep the next chunk in flight while the
 // current one is scanned, so HBM traffic is the algorithmic 2*U bytes per utterance.
 //   * noise_atap: from the first staged chunk, three lanes per 240-sample block (IDP.2A sums, 16-byte loads);
