@@ -411,6 +411,7 @@ def main():
     import sr_b200
     # NUMA: run this rank (and every thread it creates: CUDA's, the packer pool's) on the socket its GPU hangs off, before
     # anything allocates; pinned buffers below come from sr_host_alloc_dev (pages on that node)
+    orig_affinity = os.sched_getaffinity(0)
     bound_node = sr_b200.lib().sr_bind_thread_to_device(local) if sr_b200.lib().sr_device_count() > local else -1
     import torch
     import torch.distributed as dist
@@ -672,6 +673,7 @@ def main():
     cpu = None
     parity = None
     if not args.no_cpu:
+        os.sched_setaffinity(0, orig_affinity)           # the CPU arm may use every core the job has, not just the GPU's socket
         cores = args.ref_procs if args.ref_procs > 0 else usable_cores()
         S = min(B, args.cpu_sample_per_core * cores)
         pcm_s = pcm[:S].cpu().numpy().view(np.uint16)
