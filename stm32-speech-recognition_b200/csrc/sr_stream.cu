@@ -320,6 +320,7 @@ static int streams_push_impl(sr_stream_pool *p, const uint16_t *chunk, uint32_t 
     SR_REQUIRE(h, max_len == 0 || chunk != nullptr);
     SR_REQUIRE(h, max_len <= p->L && chunk_stride >= max_len);
     DeviceGuard g(h->device);
+    if (h->comm) { const int rc = sr_comm_wait(h); if (rc) return rc; }   // a pending gather may still read the handle's key buffer
     const u16 *chunk_dev = static_cast<const u16 *>(p->stage.p);
     u32 chunk_dev_stride = p->stage_stride;
     if (max_len) {

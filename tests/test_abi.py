@@ -96,3 +96,42 @@ def test_wav_ingestion_matches_the_documented_mapping(tmp_path):
         atap = o.noise_atap(pcm[:16000].copy(), 2400)
         seg = o.vad(pcm[:16000].copy(), min(len(pcm), 16000), atap)
         assert seg[0] != ob.NULL                       # the reference's VAD opens a segment on its own recording
+
+
+def test_command_labels_without_a_device():
+    """commstr[] of main.c:25-31 (what spch_recg returns, main.c:295): the reference's own 18 labels are built in and
+    need neither a handle nor a GPU; sr_labels_batch maps failed utterances to NULL like spch_recg's early returns"""
+    import ctypes as C
+    import numpy as np
+    import sr_b200
+    L = sr_b200.lib()
+    L.sr_label.argtypes = [C.c_void_p, C.c_uint32]
+    L.sr_label.restype = C.c_void_p
+    got = [C.string_at(L.sr_label(None, k)) for k in range(18)]
+    assert got[:10] == [b"%d " % k for k in range(10)]
+    assert [g.decode("gbk") for g in got[10:]] == ["上", "下", "前", "后", "左", "右", "大", "小"]
+    assert L.sr_label(None, 18) is None and L.sr_label(None, 2 ** 31) is None
+    L.sr_labels_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    cmd = np.array([3, 17, 5, 40], np.uint32)
+    st = np.array([0, 0, 1, 0], np.uint8)
+    out = (C.c_void_p * 4)()
+    assert L.sr_labels_batch(None, cmd.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p), 4, out) == 0
+    assert C.string_at(out[0]) == b"3 " and C.string_at(out[1]).decode("gbk") == "小" and out[2] is None and out[3] is None
+
+
+def test_placement_helpers_degrade_without_a_device():
+    """no CUDA device: the NUMA helpers report 'unknown' instead of failing, and never touch the calling thread"""
+    import ctypes as C
+    import os
+    import numpy as np
+    import sr_b200
+    L = sr_b200.lib()
+    if L.sr_device_count() != 0:
+        import pytest
+        pytest.skip("a CUDA device is present")
+    before = os.sched_getaffinity(0)
+    assert L.sr_device_numa_node(0) == -1
+    assert L.sr_bind_thread_to_device(0) == -1
+    assert os.sched_getaffinity(0) == before
+    a = np.ones(4096, np.uint8)
+    assert L.sr_host_numa_node(a.ctypes.data_as(C.c_void_p)) >= -1
