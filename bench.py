@@ -297,7 +297,10 @@ def run_kernel_workload(args):
         line.update({"data": "synthetic", "config": {"workload": line.pop("workload")}, "gpu_launches": h.launch_count()})
         print(json.dumps(line))
         return
-    if args.workload == "mfcc":
+    if args.workload in ("mfcc", "mfcc_b"):
+        geom_b = args.workload == "mfcc_b"               # GEOM_B extension (200/80/256): parity unpinned, own oracle
+        if geom_b:
+            h.set_geometry(1)
         pcm = torch.empty((B, U), dtype=torch.int16, device=dev)
         sr_b200.synth_pcm_dev(pcm.data_ptr(), B, U, SEED, 1, stream.cuda_stream)
         seg = torch.tensor([80, 8000], dtype=torch.int32, device=dev).repeat(B, 1).contiguous()
@@ -306,19 +309,28 @@ def run_kernel_workload(args):
         atap = torch.from_numpy(atap_h.view(np.uint8).reshape(B, 12)).to(dev)
         ftr = torch.zeros((B, 2860), dtype=torch.uint8, device=dev)
         run = lambda: h.mfcc_dev(pcm.data_ptr(), U, B, seg.data_ptr(), 2, atap.data_ptr(), ftr.data_ptr())
-        units, unit_name = B * 98.0, "MFCC frames/s"
-        bytes_per_launch = B * (2.0 * 7921 + 24 * 98 + 4)
+        nfr = (7920 - 200) // 80 + 1 if geom_b else 98
+        units, unit_name = B * float(nfr), "MFCC frames/s"
+        bytes_per_launch = B * (2.0 * 7921 + 24 * nfr + 4)
         S = min(B, 64 * cores)
         o = ob.best_oracle()
         pcm_s = pcm[:S].cpu().numpy().view(np.uint16)
         seg_s = np.tile(np.array([80, 8000], np.uint32), (S, 1))
         t0 = time.perf_counter()
-        ref = o.mfcc_batch(pcm_s, seg_s, atap_h[:S], nthreads=cores) if o.name == "oracle-port" else o.mfcc_batch(pcm_s, seg_s, atap_h[:S])
+        if geom_b:
+            o = ob.port()
+            ref = o.mfcc_geom_b_batch(pcm_s, seg_s, atap_h[:S])
+        else:
+            ref = o.mfcc_batch(pcm_s, seg_s, atap_h[:S], nthreads=cores) if o.name == "oracle-port" else o.mfcc_batch(pcm_s, seg_s, atap_h[:S])
         cpu_s = time.perf_counter() - t0
-        cpu = {"value": S * 98 / cpu_s, "unit": unit_name, "cores": cores if o.name == "oracle-port" else 1, "kind": "port" if o.name == "oracle-port" else "reference",
+        cpu = {"value": S * nfr / cpu_s, "unit": unit_name, "cores": cores if o.name == "oracle-port" else 1, "kind": "port" if o.name == "oracle-port" else "reference",
                "sample": "first %d utterances (fixed segment), single call" % S}
         check = lambda: ob.ftr_equal(ftr[:S].cpu().numpy().view(sr_b200.FTR_DTYPE).reshape(-1), ref)
         cfg = "configs[1] kernel view: 65536 x 1 s, fixed segment [80,8000) -> 98 frames/utt, mid 2048 (SURVEY 8d config 2)"
+        if geom_b:
+            cpu["cores"], cpu["kind"] = 1, "port"
+            checker = "own restatement sro_mfcc_geom_b (GEOM_B is an extension: parity unpinned by the reference)"
+            cfg = "GEOM_B extension (200/80/256, BASELINE configs[0] framing): 65536 x 1 s, fixed segment [80,8000) -> %d frames/utt" % nfr
     else:
         T = args.templates if args.templates != 20 else 200
         fin = torch.from_numpy(sr_b200.synth_ftr_host(B, 0xD7A00000, 50, 100)).to(dev)
@@ -386,7 +398,7 @@ def main():
     ap.add_argument("--ref-sample-per-core", type=int, default=128, help="--impl reference: utterances per core per step")
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU worker count (0 = usable cores: affinity capped by cgroup quota)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="recognise", choices=["recognise", "mfcc", "dtw", "dtw_band", "stream"])
+    ap.add_argument("--workload", default="recognise", choices=["recognise", "mfcc", "mfcc_b", "dtw", "dtw_band", "stream"])
     ap.add_argument("--streams", type=int, default=8192)
     ap.add_argument("--dtw-variant", type=int, default=-1, help="greedy dtw kernel: 0 static, 1 dynamic pair scheduling, -1 library default")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3], help="1 = BASELINE configs[1] per GPU (default); 3 = configs[3]: 131072 utterances per GPU x 50 templates")
