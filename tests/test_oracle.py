@@ -154,3 +154,81 @@ def test_generic_radix4_fft_reproduces_the_1024_point_restatement():
         exact = np.fft.fft(tone) / N
         assert np.abs(re - exact.real).max() <= 8 and np.abs(im - exact.imag).max() <= 8
         assert abs(re[5] - 4000) <= 8 and abs(re[N - 5] - 4000) <= 8
+
+
+def test_bitmap_endpoint_fsm_equals_sequential_fsm_on_every_prefix():
+    """The endpoint FSM of VAD.C:164-216 as the kernels evaluate it (sr_vad_core.cuh::fsm_segments: 8 consecutive active
+    frames open a segment at the first of them, 11 consecutive inactive frames close it at the first of those, at most 3
+    segments) against the sequential state machine -- on random activity patterns and on EVERY prefix of them, which is the
+    property the streaming kernel relies on: re-running the bitmap form on the frames seen so far yields exactly the
+    decisions the sequential FSM has taken by then."""
+    rng = np.random.default_rng(164)
+
+    def sequential(act):
+        seg = [None] * 6
+        cur = front = back = con = 0
+        for k, a in enumerate(act):
+            i = 80 * k
+            if a:                                               # VAD.C:164-187
+                if cur == 0:
+                    cur, front = 1, 1
+                elif cur == 1:
+                    front += 1
+                    if front >= 8:
+                        cur, seg[2 * con], front = 2, i - 7 * 80, 0
+                elif cur == 3:
+                    back, cur = 0, 2
+            else:                                               # VAD.C:188-216
+                if cur == 2:
+                    cur, back = 3, 1
+                elif cur == 3:
+                    back += 1
+                    if back >= 11:
+                        cur, back = 0, 0
+                        seg[2 * con + 1] = i - 11 * 80 + 160
+                        con += 1
+                        if con == 3:
+                            break
+                elif cur == 1:
+                    front, cur = 0, 0
+        return seg
+
+    def bitmap(act):
+        n = len(act)
+        aw = sum(1 << k for k, a in enumerate(act) if a)
+        vmask = (1 << n) - 1
+        a8 = aw
+        for s in (1, 2, 4):
+            a8 &= a8 >> s
+        z = ~aw & vmask
+        z8 = z
+        for s in (1, 2, 4):
+            z8 &= z8 >> s
+        z11 = z8 & (z8 >> 3)
+        seg, cur = [None] * 6, 0
+
+        def first(bits, frm):
+            bits >>= frm
+            return -1 if bits == 0 else frm + (bits & -bits).bit_length() - 1
+        for sgi in range(3):
+            p = first(a8, cur)
+            if p < 0:
+                break
+            seg[2 * sgi] = 80 * p
+            q = first(z11, p + 8)
+            if q < 0:
+                break
+            seg[2 * sgi + 1] = 80 * q + 80
+            cur = q + 11
+        return seg
+
+    for trial in range(60):
+        n = int(rng.integers(1, 500))
+        p_on = float(rng.choice([0.1, 0.5, 0.8, 0.95]))
+        act, state = [], 0
+        for _ in range(n):                                       # bursty activity: runs of speech and silence
+            if rng.random() < 0.08:
+                state ^= 1
+            act.append(bool(state) if rng.random() < p_on else bool(rng.integers(0, 2)))
+        for m in list(range(0, n + 1, 7)) + [n]:
+            assert bitmap(act[:m]) == sequential(act[:m]), (trial, m)
