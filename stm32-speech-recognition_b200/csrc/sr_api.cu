@@ -79,7 +79,7 @@ int sr_destroy(sr_handle *h) {
     delete h->pool;
     for (void *&st : h->stage) if (st) { cudaFreeHost(st); st = nullptr; }
     DevBuf *bufs[] = {&h->dpacked, &h->bank_own, &h->pcm, &h->atap, &h->seg, &h->ftr, &h->score, &h->best, &h->best_alt, &h->status,
-                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2, &h->dtw_scratch, &h->bank_perm, &h->vad_work};
+                      &h->bidx, &h->bdis, &h->cmd, &h->misc0, &h->misc1, &h->misc2, &h->dtw_scratch, &h->bank_perm, &h->vad_work, &h->mfcc_work};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

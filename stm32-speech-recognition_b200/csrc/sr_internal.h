@@ -16,7 +16,7 @@ cudaError_t launch_vad(const u16 *pcm, u32 U, u32 B, u32 n_len, u32 buf_len, int
                        u32 *seg_off, int num_sms, cudaStream_t st, u32 *work = nullptr);
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
                         int num_sms, cudaStream_t st, const u32 *row_map = nullptr, u32 rows_total = 0,
-                        const u32 *B_dev = nullptr);
+                        const u32 *B_dev = nullptr, u32 *work = nullptr);
 cudaError_t launch_mfcc_geomb(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap, void *ftr,
                               int num_sms, cudaStream_t st, const u32 *row_map = nullptr, const u32 *B_dev = nullptr);
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
@@ -93,6 +93,7 @@ struct sr_handle {
     u32 n_labels = 0, label_stride = 0;
     sr_comm *comm = nullptr;                           // the exchange step (sr_comm_create), optional
     int dtw_variant = -1;                              // greedy dtw kernel: 0 static lane = pair (sr_dtw.cu), 1 dynamic pairs (sr_dtw_dyn.cu), -1 default
+    DevBuf mfcc_work;                                  // the same for mfcc_kernel (next utterance, CTAs finished)
     DevBuf vad_work;                                   // two words: dynamic utterance hand-out of vad_kernel (zeroed once, self re-arming)
     DevBuf dtw_scratch;                                // one word: max frm_num of the current inputs (dynamic kernel's slot size)
     int geom = 0;                                      // SR_GEOM_REF (160/80/1024) or SR_GEOM_B (200/80/256, extension)
@@ -130,11 +131,19 @@ inline cudaError_t ensure(DevBuf &b, size_t bytes) {
     return cudaSuccess;
 }
 
+inline u32 *mfcc_work(sr_handle *h) {
+    if (!h->mfcc_work.p) {
+        if (ensure(h->mfcc_work, 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaMemsetAsync(h->mfcc_work.p, 0, 16, h->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    return static_cast<u32 *>(h->mfcc_work.p);
+}
+
 // get_mfcc in the handle's geometry
 inline cudaError_t launch_mfcc_h(sr_handle *h, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
                                  void *ftr, const u32 *row_map = nullptr, u32 rows_total = 0, const u32 *B_dev = nullptr) {
     if (h->geom == 1) return launch_mfcc_geomb(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, B_dev);
-    return launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, rows_total, B_dev);
+    return launch_mfcc(pcm, U, B, seg, seg_stride, atap, ftr, h->num_sms, h->stream, row_map, rows_total, B_dev, mfcc_work(h));
 }
 
 // the handle's work counters for vad_kernel (allocated and zeroed on first use)

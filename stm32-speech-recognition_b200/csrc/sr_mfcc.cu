@@ -28,6 +28,7 @@
 // The generic kernel below keeps the wrap because it accepts arbitrary complex input.
 #include <stdio.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "sr_common.cuh"
 
 #ifndef SR_MFCC_DEFAULT_WARPS
@@ -51,7 +52,7 @@ struct __align__(16) MfccSmem {
     u32 lg[kConsumerWarps][32];
     u64 full[kNBuf];
     u64 empty[kNBuf];
-    s32 meta[kNBuf][4];                      // {F, sample index of x[start-1] in the buffer, mid, -}
+    s32 meta[kNBuf][4];                      // {F (-1 = no more utterances), sample index of x[start-1] in the buffer, mid, utterance b}
 };
 
 __device__ __forceinline__ int padF(int e) { return e + ((e >> 6) << 2); }
@@ -94,7 +95,7 @@ __device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> 
     const int F = mfcc_frames(st, en, U);
     if (lane == 0) *reinterpret_cast<u16 *>(ftr + (size_t)b * kFtrBytes + 2) = (u16)F;   // MFCC.C:106,189
     if (F == 0) {
-        if (lane == 0) { sm.meta[s][0] = 0; sm.meta[s][1] = 0; sm.meta[s][2] = (s32)mid; mbar_arrive(&sm.full[s]); }
+        if (lane == 0) { sm.meta[s][0] = 0; sm.meta[s][1] = 0; sm.meta[s][2] = (s32)mid; sm.meta[s][3] = (s32)b; mbar_arrive(&sm.full[s]); }
         return;
     }
     long long first = row * U + st - 1;                    // may be -1 for row 0, start 0
@@ -115,7 +116,7 @@ __device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> 
         const u32 nbytes = (u32)(hi_al - lo_al);
         const int shift = (int)((lo - lo_al) >> 1);
         if (lane == 0) {
-            sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid;
+            sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid; sm.meta[s][3] = (s32)b;
             sm.meta[s][1] = (off ? 7 : shift);             // index of x[start-1] (7 = slot just below dst+16)
         }
         // tail beyond the last whole 16-byte granule of the allocation: plain loads
@@ -137,10 +138,21 @@ __device__ __forceinline__ void stage_utterance(MfccSmem<kConsumerWarps, kNBuf> 
         for (int i = lane; i < n; i += 32) d[i] = g[i];
         __syncwarp();
         if (lane == 0) {
-            sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid; sm.meta[s][1] = off ? 7 : 0;
+            sm.meta[s][0] = F; sm.meta[s][2] = (s32)mid; sm.meta[s][1] = off ? 7 : 0; sm.meta[s][3] = (s32)b;
             mbar_arrive(&sm.full[s]);
         }
     }
+}
+
+// end-of-work marker in ring slot it % kNBuf: consumers leave their loop when they meet it
+template <int kConsumerWarps, int kNBuf, bool kRelaxedWait>
+__device__ __forceinline__ void stage_end(MfccSmem<kConsumerWarps, kNBuf> &sm, int it, int lane) {
+    const int s = it % kNBuf;
+    if (it >= kNBuf) {
+        if (kRelaxedWait) mbar_wait_relaxed(&sm.empty[s], ((it / kNBuf) - 1) & 1);
+        else mbar_wait(&sm.empty[s], ((it / kNBuf) - 1) & 1);
+    }
+    if (lane == 0) { sm.meta[s][0] = -1; mbar_arrive(&sm.full[s]); }
 }
 
 // kSelf = false: warp kConsumerWarps is a dedicated producer. kSelf = true: every warp is a consumer and the staging
@@ -150,10 +162,18 @@ template <int kConsumerWarps, int kNBuf, bool kSelf>
 __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u32 B, const u32 *__restrict__ seg,
                                           u32 seg_stride, const atap_tag *__restrict__ atap,
                                           unsigned char *__restrict__ ftr, const DevTables *__restrict__ tab,
-                                          const u32 *__restrict__ row_map, u32 rows_total, const u32 *__restrict__ B_dev) {
-    constexpr int kAhead = kNBuf - 2;
+                                          const u32 *__restrict__ row_map, u32 rows_total, const u32 *__restrict__ B_dev,
+                                          u32 *__restrict__ work /* [0] next utterance to hand out, [1] CTAs finished; NULL: static */) {
+    constexpr int kAhead = kNBuf - 2;                      // slot of it+kAhead was last used by utterance it-2
     if (B_dev) B = min(B, *B_dev);                         // batch size produced on the device (streaming: segments closed by this push)
-    if (blockIdx.x >= B) return;                      // slot of it+kAhead was last used by utterance it-2
+    // the last CTA out re-arms the hand-out counters for the next launch on this stream
+    auto cta_done = [&]() {
+        if (work && threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&work[1], 1u) == gridDim.x - 1u) { work[0] = 0; work[1] = 0; }
+        }
+    };
+    if (blockIdx.x >= B) { cta_done(); return; }           // more CTAs than utterances (device-side batch size): these never claim
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MfccSmem<kConsumerWarps, kNBuf> &sm = *reinterpret_cast<MfccSmem<kConsumerWarps, kNBuf> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,20 +198,29 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     const size_t total_bytes = (size_t)(row_map ? rows_total : B) * U * 2;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
 
+    // Utterances are handed out dynamically (one atomic per utterance per CTA) when `work` is given: CTAs whose utterances
+    // happen to hold more frames, or that start late, take fewer; statically strided CTAs ended up to 2 % apart.
+    // Stage utterance number `it_s` of this CTA's sequence (or the end marker), executed by one warp.
+    auto claim_stage = [&](int it_s, auto relaxed) {
+        u32 b;
+        if (work) { b = 0; if (lane == 0) b = atomicAdd(&work[0], 1u); b = __shfl_sync(0xFFFFFFFFu, b, 0); }
+        else b = blockIdx.x + (u32)it_s * gridDim.x;
+        if (b < B)
+            stage_utterance<kConsumerWarps, kNBuf, decltype(relaxed)::value>(sm, it_s, b, pcm, U, seg, seg_stride, atap, ftr, row_map,
+                                                                            total_bytes, base_aligned, lane);
+        else
+            stage_end<kConsumerWarps, kNBuf, decltype(relaxed)::value>(sm, it_s, lane);
+        return b < B;
+    };
     if (!kSelf) {
         // ============================ producer warp =============================================
         if (warp == kConsumerWarps) {
-            int it = 0;
-            for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it)
-                stage_utterance<kConsumerWarps, kNBuf, true>(sm, it, b, pcm, U, seg, seg_stride, atap, ftr, row_map,
-                                                             total_bytes, base_aligned, lane);
+            for (int it = 0;; ++it)
+                if (!claim_stage(it, std::true_type{})) break;
             return;
         }
     } else if (warp < kAhead) {                            // prologue: utterances 0 .. kAhead-1
-        const u32 b = blockIdx.x + (u32)warp * gridDim.x;
-        if (b < B)
-            stage_utterance<kConsumerWarps, kNBuf, false>(sm, warp, b, pcm, U, seg, seg_stride, atap, ftr, row_map,
-                                                          total_bytes, base_aligned, lane);
+        claim_stage(warp, std::false_type{});
     }
 
     // ================================ consumer warps ============================================
@@ -216,17 +245,13 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     for (int i = 0; i < 12; ++i) dctk[i] = (lane < 24) ? (s32)tab->dct[(lane >> 1) * 24 + (lane & 1) * 12 + i] : 0;
 
     u32 gidx = 0;   // frames of this CTA's stream before the current utterance
-    int it = 0;
-    for (u32 b = blockIdx.x; b < B; b += gridDim.x, ++it) {
-        if (kSelf && warp == it % kConsumerWarps) {
-            const u32 bn = b + (u32)kAhead * gridDim.x;
-            if (bn < B)
-                stage_utterance<kConsumerWarps, kNBuf, false>(sm, it + kAhead, bn, pcm, U, seg, seg_stride, atap, ftr,
-                                                              row_map, total_bytes, base_aligned, lane);
-        }
+    for (int it = 0;; ++it) {
+        if (kSelf && warp == it % kConsumerWarps) claim_stage(it + kAhead, std::false_type{});
         const int s = it % kNBuf;
         mbar_wait(&sm.full[s], (it / kNBuf) & 1);
         const int F = sm.meta[s][0];
+        if (F < 0) break;                                                  // end marker: no more utterances for this CTA
+        const u32 b = (u32)sm.meta[s][3];
         const int off = sm.meta[s][1];
         const s32 mid = sm.meta[s][2];
         const u16 *x = reinterpret_cast<const u16 *>(sm.pcm[s]) + off;   // x[0] = sample start-1
@@ -395,6 +420,8 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
+    __syncthreads();                                   // every warp has made its last claim: only now may the counters be re-armed
+    cta_done();
 }
 
 // Variants (one persistent CTA per SM; threads per CTA are capped at floor(65536 / regs / 128) * 128):
@@ -412,8 +439,8 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
                                                          unsigned char *__restrict__ ftr,                         \
                                                          const DevTables *__restrict__ tab,                       \
                                                          const u32 *__restrict__ row_map, u32 rows_total,        \
-                                                         const u32 *__restrict__ B_dev) {                         \
-        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev);           \
+                                                         const u32 *__restrict__ B_dev, u32 *__restrict__ work) { \
+        mfcc_body<W, NB, SELF>(pcm, U, B, seg, seg_stride, atap, ftr, tab, row_map, rows_total, B_dev, work);     \
     }
 SR_MFCC_VARIANT(s16, 16, 4, true, 128)
 SR_MFCC_VARIANT(w15, 15, 3, false, 128)
@@ -474,14 +501,14 @@ fft_generic_kernel(const u32 *__restrict__ in /*[n][1024] packed or NULL*/, cons
 template <int W, int NB, bool SELF, typename K>
 static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride,
                                        const atap_tag *atap, void *ftr, int num_sms, const DevTables *tab, cudaStream_t st,
-                                       const u32 *row_map, u32 rows_total, const u32 *B_dev) {
+                                       const u32 *row_map, u32 rows_total, const u32 *B_dev, u32 *work) {
     const size_t smem = sizeof(MfccSmem<W, NB>);
     const int threads = (SELF ? W : W + 1) * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const u32 grid = B < (u32)num_sms ? B : (u32)num_sms;
     kern<<<grid, threads, smem, st>>>(pcm, U, B, seg, seg_stride, atap, static_cast<unsigned char *>(ftr), tab, row_map,
-                                      rows_total, B_dev);
+                                      rows_total, B_dev, work);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
@@ -494,7 +521,7 @@ static cudaError_t launch_mfcc_variant(K kern, const u16 *pcm, u32 U, u32 B, con
 }
 
 cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_stride, const atap_tag *atap,
-                        void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total, const u32 *B_dev) {
+                        void *ftr, int num_sms, cudaStream_t st, const u32 *row_map, u32 rows_total, const u32 *B_dev, u32 *work) {
     if (B == 0) return cudaSuccess;
     const DevTables *tab = dev_tables();
     if (!tab) return cudaErrorInitializationError;
@@ -504,8 +531,8 @@ cudaError_t launch_mfcc(const u16 *pcm, u32 U, u32 B, const u32 *seg, u32 seg_st
         variant = ev ? atoi(ev) : SR_MFCC_DEFAULT_WARPS;
     }
     if (variant == 15)
-        return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
-    return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev);
+        return launch_mfcc_variant<15, 3, false>(mfcc_kernel_w15, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev, work);
+    return launch_mfcc_variant<16, 4, true>(mfcc_kernel_s16, pcm, U, B, seg, seg_stride, atap, ftr, num_sms, tab, st, row_map, rows_total, B_dev, work);
 }
 
 cudaError_t launch_fft_generic(const u32 *in_packed, const s16 *frames, u32 len, u32 n, u32 *raw_out, u32 *mag,
