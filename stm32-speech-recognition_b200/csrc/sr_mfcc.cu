@@ -53,6 +53,7 @@ struct __align__(16) MfccSmem {
     u64 full[kNBuf];
     u64 empty[kNBuf];
     s32 meta[kNBuf][4];                      // {F (-1 = no more utterances), sample index of x[start-1] in the buffer, mid, utterance b}
+    int turn;                                // dynamic hand-out: number of the CTA's next claim (claims are made in ring order)
 };
 
 __device__ __forceinline__ int padF(int e) { return e + ((e >> 6) << 2); }
@@ -190,6 +191,7 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     for (int i = threadIdx.x; i < kConsumerWarps; i += blockDim.x) sm.fftbuf[i][kFltZero] = 0u;   // S(512)'s in-lane part
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNBuf; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
+        sm.turn = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -201,9 +203,23 @@ __device__ __forceinline__ void mfcc_body(const u16 *__restrict__ pcm, u32 U, u3
     // Utterances are handed out dynamically (one atomic per utterance per CTA) when `work` is given: CTAs whose utterances
     // happen to hold more frames, or that start late, take fewer; statically strided CTAs ended up to 2 % apart.
     // Stage utterance number `it_s` of this CTA's sequence (or the end marker), executed by one warp.
+    // The claims of one CTA are made by different warps, so they take turns in ring order: the counter only grows, hence
+    // the utterance numbers of a CTA grow with it_s and every slot behind an end marker holds an end marker too (a later
+    // slot claimed EARLIER could hold a real utterance that the consumers, leaving at the first marker, would never see).
+    // A claim waits only for the claim before it, which is made at the top of an earlier iteration: no cycle.
     auto claim_stage = [&](int it_s, auto relaxed) {
         u32 b;
-        if (work) { b = 0; if (lane == 0) b = atomicAdd(&work[0], 1u); b = __shfl_sync(0xFFFFFFFFu, b, 0); }
+        if (work) {
+            b = 0;
+            if (lane == 0) {
+                volatile int *turn = &sm.turn;
+                while (*turn != it_s) { }
+                b = atomicAdd(&work[0], 1u);
+                __threadfence_block();
+                if (b != 0xFFFFFFFFu) *turn = it_s + 1;                    // (the test makes the store wait for the atomic's result)
+            }
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        }
         else b = blockIdx.x + (u32)it_s * gridDim.x;
         if (b < B)
             stage_utterance<kConsumerWarps, kNBuf, decltype(relaxed)::value>(sm, it_s, b, pcm, U, seg, seg_stride, atap, ftr, row_map,
