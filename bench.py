@@ -657,12 +657,17 @@ def main():
     sha = kernel_source_sha()
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-        if tj.get("kernel_source_sha") != sha:
+        # "carried" lists later source hashes for which the capture still stands, each with the stated reason (a change
+        # that moves no byte and no per-frame instruction); any other hash is stale
+        carried = {c["sha"]: c["why"] for c in tj.get("carried", [])}
+        if tj.get("kernel_source_sha") != sha and sha not in carried:
             traffic_src = "stale: profiles/r2_traffic.json was captured for kernel sources %s, this tree is %s" % (tj.get("kernel_source_sha"), sha)
             tj = None
         elif B == tj.get("batch") and T == tj.get("templates"):
             traffic = [v["dram_bytes_per_launch"] for k, v in tj["kernels"].items() if k.startswith("mfcc_kernel")][0]
             traffic_src = tj["source"]
+            if sha in carried:
+                traffic_src += " | captured for sources %s, carried to %s: %s" % (tj.get("kernel_source_sha"), sha, carried[sha])
     except Exception:
         tj = None
     vad_bytes = (2.0 * U + 24.0) * B                    # K0: 2*U read + 24 B written per utterance
