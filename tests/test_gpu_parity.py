@@ -115,6 +115,25 @@ def test_mfcc_unaligned_utterance_stride(handle, ora, U):
     assert ob.ftr_equal(handle.mfcc(pcm, seg, atap), ora.mfcc_batch(pcm, seg, atap))
 
 
+@pytest.mark.parametrize("B", [1, 2, 37, 147, 148, 149, 295, 296, 297, 445, 1000])
+def test_mfcc_batch_sizes_around_the_cta_count(handle, ora, B):
+    """mfcc_kernel hands utterances out with an atomic counter and ends a CTA's walk with an end marker in its staging
+    ring; batch sizes around 1x / 2x / 3x the CTA count make every mix of (utterance, marker) land in a CTA's first
+    ring slots, in either claim order (the first version lost an utterance that sat behind a marker). Run twice: the
+    last CTA out re-arms the counter for the next launch."""
+    U = 4003
+    pcm = sr_b200.synth_pcm_host(B, U, 0x4A00 + B)
+    rng = np.random.default_rng(B)
+    st = rng.integers(1, 900, B)
+    en = np.minimum(st + rng.integers(160, 3000, B), U)
+    seg = np.stack([st, en], 1).astype(np.uint32)
+    atap = np.zeros(B, sr_b200.ATAP_DTYPE)
+    atap["mid_val"] = 2000
+    want = ora.mfcc_batch(pcm, seg, atap)
+    for _ in range(2):
+        assert ob.ftr_equal(handle.mfcc(pcm, seg, atap), want)
+
+
 def test_mfcc_segment_at_sample_zero_reads_previous_utterance(handle, ora):
     """start == 0 makes MFCC.C:119 read vc_dat[-1]; for b > 0 that is the last sample of utterance b-1 in a
     contiguous batch (same as the reference on the same memory); for b == 0 it is pinned to mid_val."""
