@@ -99,6 +99,9 @@ typedef struct sr_handle sr_handle;
 
 int         sr_create(int device, sr_handle **out);       /* device ordinal; <0 = current device     */
 int         sr_destroy(sr_handle *h);
+/* A handle's device scratch (segments, features, scores, the kernels' utterance hand-out counters) serves ONE stream at a
+ * time: sr_sync (or order the new stream behind the old one) before switching streams; concurrent streams take one handle
+ * each -- handles are cheap, the tables are per device. */
 int         sr_set_stream(sr_handle *h, void *cuda_stream /* cudaStream_t used verbatim; NULL = legacy default stream */);
 int         sr_use_own_stream(sr_handle *h);              /* back to the handle's private non-blocking stream (the default) */
 int         sr_sync(sr_handle *h);
